@@ -1,0 +1,99 @@
+// hbv_cabi.cu — extern "C" entry points, argument validation, error text, launch accounting.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include "hbv_common.cuh"
+
+namespace hbv {
+
+static thread_local char g_err[256] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int fwd_dispatch(const hbv_desc_t* desc, const hbv_fwd_io_t* io, cudaStream_t st);
+int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st);
+
+static int expected_npar(int variant, int betaet) {
+    switch (variant) {
+        case HBV_VARIANT_HBV: return betaet ? 13 : 12;
+        case HBV_VARIANT_HBV11P: return 14;
+        case HBV_VARIANT_HBV2: return 16;
+        case HBV_VARIANT_HOURLY: return 19;
+    }
+    return -1;
+}
+
+// basins per CTA: 128-256 threads when there is enough work, fewer for small problems so the
+// grid still covers the 148 SMs (SURVEY.md §7 "low parallelism configs")
+static int choose_bpb(int B, int nmul) {
+    int bpb = 128 / nmul;
+    if (bpb < 1) bpb = 1;
+    while (bpb > 1 && (B + bpb - 1) / bpb < 2 * 148) bpb >>= 1;
+    // keep at least one full warp per CTA where possible
+    while (bpb * nmul < 32 && bpb * 2 * nmul <= 128 && bpb * 2 <= B) bpb <<= 1;
+    return bpb;
+}
+
+int make_kdesc(const hbv_desc_t* s, KDesc& d) {
+    if (!s) { set_error("null descriptor"); return HBV_E_NULL; }
+    if (s->abi_version != HBV_B200_ABI_VERSION) { set_error("ABI version mismatch"); return HBV_E_ABI; }
+    const int np = expected_npar(s->variant, s->betaet);
+    if (np < 0) { set_error("unknown variant"); return HBV_E_VARIANT; }
+    if (s->n_par != np) { set_error("n_par does not match variant"); return HBV_E_SHAPE; }
+    if (s->T <= 0 || s->B <= 0 || s->nvar <= 0 || s->dyn_ncol < 0 || s->sta_ncol < 0) { set_error("non-positive dimension"); return HBV_E_SHAPE; }
+    if (s->nmul <= 0 || s->nmul > 256) { set_error("nmul must be in [1, 256]"); return HBV_E_NMUL; }
+    if (s->i_prcp < 0 || s->i_prcp >= s->nvar || s->i_tmean < 0 || s->i_tmean >= s->nvar ||
+        s->i_pet < 0 || s->i_pet >= s->nvar) { set_error("forcing column out of range"); return HBV_E_SHAPE; }
+    if (s->ckpt_interval < 0) { set_error("negative ckpt_interval"); return HBV_E_CKPT; }
+    for (int i = 0; i < np; ++i) {
+        const int src = s->par_src[i];
+        if (src < HBV_SRC_DYN_T || src > HBV_SRC_STA) { set_error("bad par_src"); return HBV_E_SHAPE; }
+        const int ncol = (src == HBV_SRC_STA) ? s->sta_ncol : s->dyn_ncol;
+        if (s->par_col[i] < 0 || s->par_col[i] + s->nmul > ncol) { set_error("parameter column out of range"); return HBV_E_SHAPE; }
+    }
+    std::memset(&d, 0, sizeof(d));
+    d.T = s->T; d.B = s->B; d.nmul = s->nmul; d.n_par = np;
+    d.nvar = s->nvar; d.i_prcp = s->i_prcp; d.i_tmean = s->i_tmean; d.i_pet = s->i_pet;
+    d.dyn_ncol = s->dyn_ncol; d.sta_ncol = s->sta_ncol; d.apply_sigmoid = s->apply_sigmoid;
+    d.K = s->ckpt_interval; d.muwts_t_stride = s->muwts_t_stride;
+    d.nearzero = s->nearzero; d.dt = s->dt; d.inv_dt = 1.0f / s->dt;
+    d.BPB = choose_bpb(s->B, s->nmul);
+    for (int i = 0; i < np; ++i) {
+        d.src[i] = s->par_src[i]; d.col[i] = s->par_col[i];
+        d.lo[i] = s->par_lo[i]; d.span[i] = s->par_hi[i] - s->par_lo[i];
+    }
+    return 0;
+}
+
+}  // namespace hbv
+
+extern "C" {
+
+int hbv_b200_abi_version(void) { return HBV_B200_ABI_VERSION; }
+const char* hbv_b200_last_error(void) { return hbv::g_err; }
+int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
+
+int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {
+    if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (!io->forcing || !io->state_in) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
+    if (desc->variant >= HBV_VARIANT_HBV2 && !io->attrs) { hbv::set_error("attrs (Ac, Elevation) required"); return HBV_E_NULL; }
+    for (int i = 0; i < desc->n_par && i < HBV_MAX_PAR; ++i)
+        if (desc->par_src[i] == HBV_SRC_STA ? !io->sta : !io->dyn) { hbv::set_error("parameter tensor required"); return HBV_E_NULL; }
+    if (io->ckpt && desc->ckpt_interval <= 0) { hbv::set_error("ckpt buffer without ckpt_interval"); return HBV_E_CKPT; }
+    return hbv::fwd_dispatch(desc, io, (cudaStream_t)stream);
+}
+
+int hbv_b200_bwd(const hbv_desc_t* desc, const hbv_bwd_io_t* io, void* stream) {
+    if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (!io->forcing || !io->ckpt) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
+    if (desc->variant >= HBV_VARIANT_HBV2 && !io->attrs) { hbv::set_error("attrs (Ac, Elevation) required"); return HBV_E_NULL; }
+    for (int i = 0; i < desc->n_par && i < HBV_MAX_PAR; ++i)
+        if (desc->par_src[i] == HBV_SRC_STA ? (!io->sta || !io->gsta) : (!io->dyn || !io->gdyn)) { hbv::set_error("parameter tensor + gradient required"); return HBV_E_NULL; }
+    return hbv::bwd_dispatch(desc, io, (cudaStream_t)stream);
+}
+
+}  // extern "C"

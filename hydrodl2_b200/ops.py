@@ -1,0 +1,301 @@
+"""PyTorch-facing operators over the C-ABI CUDA library.
+
+``hbv_run`` is the `_PBM` replacement (hbv.py:363-596 and siblings): one
+``torch.autograd.Function`` whose forward launches K1 (fused recurrence) + K4
+(UH routing + BFI) and whose backward launches K4's adjoint + K2 (checkpointed
+adjoint of the recurrence) — no autograd tape over time steps.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all
+arithmetic happens in ``libhbv_b200.so``.  There is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi as A
+
+_ROUTED = (A.F_QSIM, A.F_Q0, A.F_Q1, A.F_Q2)
+
+
+@dataclass
+class RunSpec:
+    """Everything static about one `_PBM` call (mirrors hbv_desc_t)."""
+
+    variant: int
+    n_par: int
+    betaet: bool
+    apply_sigmoid: bool
+    par_src: Sequence[int]
+    par_col: Sequence[int]
+    par_lo: Sequence[float]
+    par_hi: Sequence[float]
+    nmul: int
+    nflux: int
+    nearzero: float = 1e-5
+    dt: float = 1.0
+    var_index: Sequence[int] = (0, 1, 2)   # prcp, tmean, pet columns
+    ckpt_interval: int = 16
+    # routing (core/calc/uh_routing.py); route_src: 'dyn_last' (packed) or 'sta' (split)
+    routing: bool = False
+    route_src: str = 'dyn_last'
+    route_col: int = 0
+    route_bounds: Sequence[Sequence[float]] = ((0, 2.9), (0, 6.5))
+    lenF: int = 15
+    n_routed: int = 4          # series routed: Qsim, Q0, Q1, Q2 (hourly: Qsim only)
+    bfi: bool = True
+    state_series: bool = False
+    extra: dict = field(default_factory=dict)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _check_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"hydrodl2_b200: `{name}` is on {t.device}; this implementation runs on CUDA "
+            "(sm_100a) only — there is no CPU path."
+        )
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"hydrodl2_b200: `{name}` must be float32, got {t.dtype}")
+
+
+def make_desc(spec: RunSpec, T: int, B: int, nvar: int, dyn_ncol: int, sta_ncol: int,
+              muwts_t_stride: int = 0) -> A.HbvDesc:
+    d = A.HbvDesc()
+    d.abi_version = A.ABI_VERSION
+    d.variant = spec.variant
+    d.T, d.B, d.nmul, d.n_par = T, B, spec.nmul, spec.n_par
+    d.betaet = int(spec.betaet)
+    d.apply_sigmoid = int(spec.apply_sigmoid)
+    d.nvar = nvar
+    d.i_prcp, d.i_tmean, d.i_pet = spec.var_index
+    d.dyn_ncol, d.sta_ncol = dyn_ncol, sta_ncol
+    for i in range(spec.n_par):
+        d.par_src[i] = spec.par_src[i]
+        d.par_col[i] = spec.par_col[i]
+        d.par_lo[i] = float(spec.par_lo[i])
+        d.par_hi[i] = float(spec.par_hi[i])
+    d.nearzero = spec.nearzero
+    d.dt = spec.dt
+    d.ckpt_interval = spec.ckpt_interval
+    d.muwts_t_stride = muwts_t_stride
+    return d
+
+
+def make_route_desc(spec: RunSpec, T: int, B: int, stride: int) -> A.HbvRouteDesc:
+    r = A.HbvRouteDesc()
+    r.abi_version = A.ABI_VERSION
+    r.T, r.B, r.lenF, r.nser = T, B, spec.lenF, spec.n_routed
+    r.apply_sigmoid = int(spec.apply_sigmoid)
+    r.route_stride = stride
+    r.bfi_num, r.bfi_den = 3, 0   # 100 * sum(Q2_rout) / (sum(Qs) + nearzero), hbv.py:562-567
+    (r.a_lo, r.a_hi), (r.b_lo, r.b_hi) = spec.route_bounds
+    r.nearzero = spec.nearzero
+    return r
+
+
+def _prep_muwts(muwts, T, B, nmul, dev):
+    """-> (contiguous tensor or None, time stride in elements)."""
+    if muwts is None:
+        return None, 0
+    if muwts.requires_grad:
+        raise NotImplementedError('hydrodl2_b200: gradients w.r.t. `muwts` are not implemented')
+    m = muwts.detach().to(device=dev, dtype=torch.float32)
+    if m.dim() == 3 and m.shape[0] == T and T > 1:
+        return m.expand(T, B, nmul).contiguous(), B * nmul
+    return m.expand(1, B, nmul).contiguous() if m.dim() == 3 else m.expand(B, nmul).contiguous(), 0
+
+
+def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None):
+    """Warm-up / `initialize=True` run (hbv.py:327-346,557-559): no flux output, no
+    checkpoints, no gradient.  Returns the final state stack [5, B, nmul]."""
+    lib = A.load()
+    _check_cuda(forcing, 'x_phy')
+    T, B, nvar = forcing.shape
+    d = make_desc(spec, T, B, nvar, 0 if dyn is None else dyn.shape[-1],
+                  0 if sta is None else sta.shape[-1])
+    d.ckpt_interval = 0
+    io = A.HbvFwdIO()
+    state_out = torch.empty_like(state_in)
+    io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn), _ptr(sta)
+    io.drop, io.attrs, io.muwts = _ptr(drop), _ptr(attrs), None
+    io.state_in, io.state_out = _ptr(state_in), _ptr(state_out)
+    with torch.cuda.device(forcing.device):
+        A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), _stream(forcing.device)), 'fwd(warm-up)')
+    return state_out
+
+
+class _HbvRun(torch.autograd.Function):
+    """K1 + K4 forward, K4^T + K2 backward."""
+
+    @staticmethod
+    def forward(ctx, spec: RunSpec, forcing, dyn, sta, state_in, drop, attrs, muwts, t_off):
+        # `dyn` is the FULL dynamic/packed tensor; rows [t_off:] belong to this run.
+        lib = A.load()
+        dev = forcing.device
+        T, B, nvar = forcing.shape
+        nmul = spec.nmul
+        dyn_run = dyn[t_off:] if dyn is not None else None
+        dyn_ncol = 0 if dyn is None else dyn.shape[-1]
+        sta_ncol = 0 if sta is None else sta.shape[-1]
+        mu, mu_ts = _prep_muwts(muwts, T, B, nmul, dev)
+        d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
+        need_grad = any(t is not None and t.requires_grad for t in (dyn, sta, state_in))
+        K = spec.ckpt_interval
+        nseg = (T + K - 1) // K
+        ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
+        if not need_grad:
+            d.ckpt_interval = 0
+
+        flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
+        state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
+        series = (torch.empty((5, T, B, nmul), device=dev, dtype=torch.float32)
+                  if spec.state_series else None)
+        io = A.HbvFwdIO()
+        io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn_run), _ptr(sta)
+        io.drop, io.attrs, io.muwts = _ptr(drop), _ptr(attrs), _ptr(mu)
+        io.state_in, io.state_out = _ptr(state_in), _ptr(state_out)
+        for f in range(spec.nflux):
+            io.flux[f] = flux[f].data_ptr()
+        io.state_series, io.ckpt = _ptr(series), _ptr(ckpt)
+        stream = _stream(dev)
+        with torch.cuda.device(dev):
+            A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), stream), 'fwd')
+
+            routed = uh = bfi = bfi_ws = None
+            rdesc = route_t = None
+            if spec.routing:
+                if spec.route_src == 'dyn_last':
+                    route_t = dyn[dyn.shape[0] - 1, :, spec.route_col:]
+                    stride = dyn_ncol
+                else:
+                    route_t = sta[:, spec.route_col:]
+                    stride = sta_ncol
+                rdesc = make_route_desc(spec, T, B, stride)
+                nch = lib.hbv_b200_route_chunks(T, B)
+                routed = torch.empty((spec.n_routed, T, B), device=dev, dtype=torch.float32)
+                uh = torch.empty((min(spec.lenF, T), B), device=dev, dtype=torch.float32)
+                if spec.bfi:
+                    bfi = torch.empty((B,), device=dev, dtype=torch.float32)
+                    bfi_ws = torch.empty((2, nch, B), device=dev, dtype=torch.float32)
+                A.check(lib.hbv_b200_route_fwd(C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(),
+                                               T * B, routed.data_ptr(), T * B, uh.data_ptr(),
+                                               _ptr(bfi), _ptr(bfi_ws), stream), 'route_fwd')
+
+        ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
+        ctx.has = (dyn is not None, sta is not None)
+        ctx.save_for_backward(forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in)
+        ctx.set_materialize_grads(False)
+        outs = [flux[f] for f in range(spec.nflux)]
+        n_r = spec.n_routed if spec.routing else 0
+        outs += [routed[s] for s in range(n_r)]
+        outs.append(bfi if bfi is not None else flux.new_zeros(()))
+        outs.append(state_out)
+        outs.append(series if series is not None else flux.new_zeros(()))
+        ctx.n_r = n_r
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = A.load()
+        spec: RunSpec = ctx.spec
+        forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in = ctx.saved_tensors
+        T, B, nvar, dyn_ncol, sta_ncol, mu_ts = ctx.dims
+        dev = forcing.device
+        nmul, nf, n_r = spec.nmul, spec.nflux, ctx.n_r
+        if ckpt is None:
+            raise RuntimeError('hydrodl2_b200: backward called but no input required grad')
+        g_flux = [None if g is None else g.contiguous() for g in grads[:nf]]
+        g_rout = grads[nf:nf + n_r]
+        g_bfi, g_state, g_series = grads[nf + n_r], grads[nf + n_r + 1], grads[nf + n_r + 2]
+        t_off = ctx.t_off
+        stream = _stream(dev)
+
+        gdyn_full = torch.zeros_like(dyn) if dyn is not None else None
+        gsta = torch.zeros_like(sta) if sta is not None else None
+        gdyn_run = gdyn_full[t_off:] if gdyn_full is not None else None
+
+        with torch.cuda.device(dev):
+            if spec.routing and (any(g is not None for g in g_rout) or g_bfi is not None):
+                mask = 0
+                g_out = torch.empty((n_r, T, B), device=dev, dtype=torch.float32)
+                for s, g in enumerate(g_rout):
+                    if g is not None:
+                        g_out[s].copy_(g)
+                        mask |= 1 << s
+                g_in = torch.empty((n_r, T, B), device=dev, dtype=torch.float32)
+                if spec.route_src == 'dyn_last':
+                    route_t = dyn[dyn.shape[0] - 1, :, spec.route_col:]
+                    g_route = gdyn_full[dyn.shape[0] - 1, :, spec.route_col:]
+                    stride = dyn_ncol
+                else:
+                    route_t = sta[:, spec.route_col:]
+                    g_route = gsta[:, spec.route_col:]
+                    stride = sta_ncol
+                rdesc = make_route_desc(spec, T, B, stride)
+                nch = lib.hbv_b200_route_chunks(T, B)
+                ws = torch.empty((min(spec.lenF, T), nch, B), device=dev, dtype=torch.float32)
+                gb = None if g_bfi is None else g_bfi.contiguous()
+                A.check(lib.hbv_b200_route_bwd(
+                    C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(), T * B, None, T * B,
+                    uh.data_ptr(), _ptr(bfi_ws), g_out.data_ptr(), T * B, mask, _ptr(gb),
+                    g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
+                for s in range(n_r):
+                    f = _ROUTED[s]
+                    g_flux[f] = g_in[s] if g_flux[f] is None else g_flux[f] + g_in[s]
+
+            d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
+            io = A.HbvBwdIO()
+            io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn[t_off:] if dyn is not None else None), _ptr(sta)
+            io.drop, io.attrs, io.muwts, io.ckpt = _ptr(drop), _ptr(attrs), _ptr(mu), _ptr(ckpt)
+            for f in range(nf):
+                io.gflux[f] = _ptr(g_flux[f])
+            gs = None if g_state is None else g_state.contiguous()
+            gser = None if (g_series is None or not spec.state_series) else g_series.contiguous()
+            io.gstate_out, io.gstate_series = _ptr(gs), _ptr(gser)
+            io.gdyn, io.gsta = _ptr(gdyn_run), _ptr(gsta)
+            gstate_in = torch.empty_like(state_in) if state_in.requires_grad else None
+            io.gstate_in = _ptr(gstate_in)
+            A.check(lib.hbv_b200_bwd(C.byref(d), C.byref(io), stream), 'bwd')
+        return (None, None, gdyn_full, gsta, gstate_in, None, None, None, None)
+
+
+def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, muwts=None,
+            t_off: int = 0):
+    """Run the recurrence (+ routing) on rows [t_off:] of `dyn`.
+
+    forcing  [T, B, nvar]  (already sliced to the run)
+    dyn      [T_total, B, dyn_ncol] full packed/dynamic tensor or None
+    sta      [B, sta_ncol] or None
+    state_in [5, B, nmul]
+    Returns dict(flux=[nflux x [T,B]], routed=[n_routed x [T,B]] or None, bfi, state_out, series).
+    """
+    _check_cuda(forcing, 'x_phy')
+    forcing = forcing.contiguous()
+    if dyn is not None:
+        _check_cuda(dyn, 'parameters')
+        dyn = dyn.contiguous()
+    if sta is not None:
+        _check_cuda(sta, 'static parameters')
+        sta = sta.contiguous()
+    outs = _HbvRun.apply(spec, forcing, dyn, sta, state_in.contiguous(), drop, attrs, muwts, t_off)
+    nf = spec.nflux
+    n_r = spec.n_routed if spec.routing else 0
+    return {
+        'flux': list(outs[:nf]),
+        'routed': list(outs[nf:nf + n_r]) if n_r else None,
+        'bfi': outs[nf + n_r] if (spec.routing and spec.bfi) else None,
+        'state_out': outs[nf + n_r + 1],
+        'series': outs[nf + n_r + 2] if spec.state_series else None,
+    }

@@ -1,0 +1,209 @@
+/*
+ * hbv_b200.h — C-ABI of the B200-native HBV recurrence + unit-hydrograph routing.
+ *
+ * This is the drop-in boundary.  The reference
+ * (mhpi/hydrodl2) has no FFI: its hot path is Python that issues ~70 ATen
+ * kernels per time step.  Each entry point below replaces one span of that
+ * Python (cited as reference file:line, paths relative to
+ * /root/reference/src/hydrodl2/) and is what a reference maintainer would
+ * bind with ctypes from inside `_PBM`.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch);
+ *     the library never allocates, never frees and keeps no global state;
+ *   - all tensors are float32, contiguous in the layouts stated below;
+ *   - `stream` is the caller's cudaStream_t (0 = legacy default stream);
+ *   - return value: 0 ok, >0 a cudaError_t from launch, <0 argument error
+ *     (HBV_E_*); functions never throw and are re-entrant / thread-safe;
+ *   - the last error text of the calling thread: hbv_b200_last_error().
+ */
+#ifndef HBV_B200_H
+#define HBV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBV_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HBV_API __attribute__((visibility("default")))
+#else
+#define HBV_API
+#endif
+
+#define HBV_MAX_PAR 20   /* physical parameters per variant (max 19 used) */
+#define HBV_MAX_FLUX 12  /* per-step flux series reduced over nmul */
+#define HBV_NSTATE 5     /* SNOWPACK, MELTWATER, SM, SUZ, SLZ (hbv.py:61-67) */
+
+/* argument errors */
+#define HBV_E_NULL (-1)
+#define HBV_E_SHAPE (-2)
+#define HBV_E_VARIANT (-3)
+#define HBV_E_NMUL (-4)
+#define HBV_E_CKPT (-5)
+#define HBV_E_ABI (-6)
+
+/* variants (which step arithmetic) */
+enum {
+    HBV_VARIANT_HBV = 0,      /* models/hbv/hbv.py:423-505            */
+    HBV_VARIANT_HBV11P = 1,   /* models/hbv/hbv_1_1p.py:422-516       */
+    HBV_VARIANT_HBV2 = 2,     /* models/hbv/hbv_2.py:464-575          */
+    HBV_VARIANT_HOURLY = 3    /* models/hbv/hbv_2_hourly.py:527-675   */
+};
+
+/* physical parameter slots — the order of `parameter_bounds`
+ * (hbv.py:88-101, hbv_1_1p.py:87-102, hbv_2.py:90-107, hbv_2_hourly.py:91-115) */
+enum {
+    HBV_P_BETA = 0, HBV_P_FC, HBV_P_K0, HBV_P_K1, HBV_P_K2, HBV_P_LP, HBV_P_PERC,
+    HBV_P_UZL, HBV_P_TT, HBV_P_CFMAX, HBV_P_CFR, HBV_P_CWH, HBV_P_BETAET, HBV_P_C,
+    HBV_P_RT, HBV_P_AC, HBV_P_F0, HBV_P_FMIN, HBV_P_ALPHA
+};
+
+/* flux slots written by hbv_b200_fwd (each a [T, B] plane, nmul-reduced) */
+enum {
+    HBV_F_QSIM = 0,   /* Q0+Q1+Q2 (+IE hourly): mean or muwts-weighted (hbv.py:494,508-511) */
+    HBV_F_Q0, HBV_F_Q1, HBV_F_Q2, HBV_F_AET, HBV_F_SWE, HBV_F_RECHARGE, HBV_F_EXCS,
+    HBV_F_EVAPFACTOR, HBV_F_TOSOIL, HBV_F_PERC, HBV_F_CAPILLARY
+};
+
+/* where a physical parameter's [0,1]/raw value is read from */
+enum {
+    HBV_SRC_DYN_T = 0,    /* dyn[t, b, col + j]      time-varying (dynamic)          */
+    HBV_SRC_DYN_LAST = 1, /* dyn[T-1, b, col + j]    static value of the packed form */
+    HBV_SRC_STA = 2       /* sta[b, col + j]         static tensor of the hbv_2 form */
+};
+
+/*
+ * Problem descriptor.  Plain data, passed by pointer, copied by the callee.
+ *
+ * Parameter addressing restates hbv.py:182-256 (packed raw tensor, sigmoid,
+ * static value = last row of the slice) and hbv_2.py:190-290 (split dynamic /
+ * static tensors already in [0,1]):
+ *     v01 = apply_sigmoid ? sigmoid(raw) : raw
+ *     par = v01 * (hi - lo) + lo                     (core/calc/utils.py:24)
+ * A dynamic parameter whose dropout mask is set for a basin reads row T-1 of
+ * `dyn` instead of row t (hbv.py:242-246, hbv_2.py:258-265).
+ */
+typedef struct hbv_desc {
+    int32_t abi_version;           /* HBV_B200_ABI_VERSION */
+    int32_t variant;               /* HBV_VARIANT_* */
+    int32_t T;                     /* time steps in this call */
+    int32_t B;                     /* basins (grid cells / units) */
+    int32_t nmul;                  /* parallel components per basin */
+    int32_t n_par;                 /* physical parameters of the variant */
+    int32_t betaet;                /* 1: evapfactor **= parBETAET (hbv.py:475-476) */
+    int32_t apply_sigmoid;         /* 1: raw parameters (hbv / hbv_1_1p) */
+    int32_t nvar;                  /* last dim of forcing */
+    int32_t i_prcp, i_tmean, i_pet;/* forcing columns (hbv.py:388-390) */
+    int32_t dyn_ncol;              /* row width of `dyn` */
+    int32_t sta_ncol;              /* row width of `sta` (0 if unused) */
+    int32_t par_src[HBV_MAX_PAR];  /* HBV_SRC_* per parameter */
+    int32_t par_col[HBV_MAX_PAR];  /* first column of parameter i in its source */
+    float par_lo[HBV_MAX_PAR];
+    float par_hi[HBV_MAX_PAR];
+    float nearzero;                /* hbv.py:54 */
+    float dt;                      /* 1 (daily) or 1/24 (hbv_2_hourly.py:58) */
+    int32_t ckpt_interval;         /* K: state checkpoint every K steps (0 = none) */
+    int32_t muwts_t_stride;        /* elements between time rows of muwts (0 = time-invariant) */
+    int32_t reserved[6];
+} hbv_desc_t;
+
+/* Forward I/O.  NULL output pointers are skipped. */
+typedef struct hbv_fwd_io {
+    const float* forcing;    /* [T, B, nvar]                              */
+    const float* dyn;        /* [T, B, dyn_ncol]                          */
+    const float* sta;        /* [B, sta_ncol] or NULL                     */
+    const uint8_t* drop;     /* [n_par, B] 0/1 dropout masks or NULL      */
+    const float* attrs;      /* [2, B]: Ac, Elevation (hbv_2 family) or NULL */
+    const float* muwts;      /* [T or 1, B, nmul] or NULL (hbv.py:508-511) */
+    const float* state_in;   /* [5, B, nmul]                              */
+    float* state_out;        /* [5, B, nmul]                              */
+    float* flux[HBV_MAX_FLUX];/* each [T, B]; all NULL = warm-up/initialize run (hbv.py:557-559) */
+    float* state_series;     /* [5, T, B, nmul] or NULL (hbv_2.py:571-575) */
+    float* ckpt;             /* [ceil(T/K), 5, B, nmul] or NULL           */
+} hbv_fwd_io_t;
+
+/* Backward I/O (hand-written adjoint of hbv_b200_fwd; replaces autograd over
+ * the unrolled loop). */
+typedef struct hbv_bwd_io {
+    const float* forcing;
+    const float* dyn;
+    const float* sta;
+    const uint8_t* drop;
+    const float* attrs;
+    const float* muwts;
+    const float* ckpt;                 /* from the forward call, same K     */
+    const float* gflux[HBV_MAX_FLUX];  /* upstream grads, each [T, B] or NULL */
+    const float* gstate_out;           /* [5, B, nmul] or NULL              */
+    const float* gstate_series;        /* [5, T, B, nmul] or NULL           */
+    float* gdyn;     /* [T, B, dyn_ncol], ZERO-INITIALISED by the caller: the
+                        kernel writes only the entries that receive gradient
+                        (row t for dynamic parameters, row T-1 for static ones) */
+    float* gsta;     /* [B, sta_ncol] or NULL                               */
+    float* gstate_in;/* [5, B, nmul] or NULL                                */
+} hbv_bwd_io_t;
+
+/* K1: fused forward recurrence + nmul aggregation (hbv.py:363-511). */
+HBV_API int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream);
+
+/* K2: checkpointed adjoint of K1. */
+HBV_API int hbv_b200_bwd(const hbv_desc_t* desc, const hbv_bwd_io_t* io, void* stream);
+
+/*
+ * K4: gamma unit hydrograph + causal convolution + BFI
+ * (core/calc/uh_routing.py:5-57, hbv.py:523-538,562-567).
+ *
+ *   route     [B, route_stride]: columns 0,1 = route_a, route_b (raw or [0,1])
+ *   q_in      nser planes [T, B] (plane stride q_stride elements)
+ *   q_out     nser planes [T, B] (plane stride out_stride)
+ *   uh        [lenF, B] workspace/output: the normalised UH weights
+ *   bfi       [B] or NULL: 100 * sum_t out[bfi_num] / (sum_t out[bfi_den] + nearzero)
+ *   bfi_ws    [2, nchunk, B] workspace when bfi != NULL (see hbv_b200_route_chunks)
+ */
+typedef struct hbv_route_desc {
+    int32_t abi_version;
+    int32_t T, B, lenF, nser;
+    int32_t apply_sigmoid;
+    int32_t route_stride;
+    int32_t bfi_num, bfi_den;   /* series indices for BFI */
+    float a_lo, a_hi, b_lo, b_hi;
+    float nearzero;
+    int32_t reserved[4];
+} hbv_route_desc_t;
+
+HBV_API int hbv_b200_route_chunks(int32_t T, int32_t B);
+
+HBV_API int hbv_b200_route_fwd(const hbv_route_desc_t* desc, const float* route,
+                       const float* q_in, int64_t q_stride, float* q_out,
+                       int64_t out_stride, float* uh, float* bfi, float* bfi_ws,
+                       void* stream);
+
+/*
+ * Adjoint of hbv_b200_route_fwd.
+ *   g_out     nser planes [T, B] or per-series NULL via g_out_mask bit s
+ *   g_bfi     [B] or NULL
+ *   g_in      nser planes [T, B] (written)
+ *   g_route   [B, route_stride]: columns 0,1 written (gradient w.r.t. the raw /
+ *             [0,1] routing parameters)
+ *   ws        workspace [ (lenF + 2) * nchunk * B ] floats
+ */
+HBV_API int hbv_b200_route_bwd(const hbv_route_desc_t* desc, const float* route,
+                       const float* q_in, int64_t q_stride, const float* q_out,
+                       int64_t out_stride, const float* uh, const float* bfi_ws,
+                       const float* g_out, int64_t g_stride, uint32_t g_out_mask,
+                       const float* g_bfi, float* g_in, int64_t gin_stride,
+                       float* g_route, float* ws, void* stream);
+
+/* misc */
+HBV_API int hbv_b200_abi_version(void);
+HBV_API const char* hbv_b200_last_error(void);
+/* number of kernels this library has launched in this process (bench accounting) */
+HBV_API int64_t hbv_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBV_B200_H */

@@ -1,0 +1,86 @@
+"""GPU parity: CUDA path (through the C-ABI) vs the reference's own outputs (golden
+fixtures produced by tests/golden/make_golden.py from the unmodified reference) and vs the
+CPU oracle on seeded inputs.  Tolerances: max-norm relative 1e-5 fluxes/states, 1e-4 grads."""
+
+import pytest
+import torch
+
+from conftest import RTOL_FLUX, RTOL_GRAD, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+PACKED = ['hbv_static', 'hbv_d2', 'hbv_d2_drop_nowarm', 'hbv_1_1p_d3', 'hbv_1_1p_d14']
+CLS = {'hbv': 'Hbv', 'hbv_1_1p': 'Hbv_1_1p'}
+
+
+def _run_packed(g, dev, ckpt=16):
+    import hydrodl2_b200 as hydrodl2
+    model = str(g['model'])
+    cls = CLS[model]
+    T, B, nmul, warm_up, seed = (int(v) for v in g['meta'])
+    M = hydrodl2.load_model(model, ver_name=cls)
+    cfg = {'warm_up': warm_up, 'dynamic_params': {cls: [str(s) for s in g['dyn']]}, 'nmul': nmul,
+           'dy_drop': float(g['dy_drop']), 'warm_up_states': bool(int(g['warm_up_states'])),
+           'ckpt_interval': ckpt}
+    m = M(cfg, device=dev)
+    x = g['x_phy'].to(dev)
+    p = g['parameters'].to(dev).requires_grad_(True)
+    torch.manual_seed(seed)
+    out = m({'x_phy': x}, p)
+    return m, out, p
+
+
+@pytest.mark.parametrize('case', PACKED)
+def test_forward_matches_reference(case):
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    m, out, _ = _run_packed(g, dev)
+    assert set(out.keys()) == set(g['out'].keys())
+    for k, ref in g['out'].items():
+        assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k}')
+    for name, s in zip(m.state_names, m.get_states()):
+        assert_close(s, g['states'][name], RTOL_FLUX, f'{case}:state {name}')
+
+
+@pytest.mark.parametrize('ckpt', [1, 8, 16, 32])
+@pytest.mark.parametrize('case', PACKED)
+def test_gradient_matches_reference(case, ckpt):
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    m, out, p = _run_packed(g, dev, ckpt)
+    loss = 0.0
+    for k, c in g['cot'].items():
+        loss = loss + (out[k] * c.to(dev)).sum()
+    loss.backward()
+    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad K={ckpt}')
+
+
+def test_streamflow_only_gradient_vs_oracle():
+    """Typical training use: loss on streamflow only (other flux grads are None)."""
+    from oracle import hbv_oracle as O
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    T, B, nmul, warm = 200, 37, 16, 40
+    dyn = ['parBETA', 'parBETAET']
+    x = O.synthetic_forcing(T, B, seed=11)
+    gen = torch.Generator().manual_seed(12)
+    p = torch.randn(T, B, 13 * nmul + 2, generator=gen)
+    pc = p.clone().requires_grad_(True)
+    ref, S = O.forward_packed('hbv', x, pc, nmul=nmul, warm_up=warm, dynamic_params=dyn)
+    ref['streamflow'].sum().backward()
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'warm_up': warm, 'dynamic_params': {'Hbv': dyn}, 'nmul': nmul}, device=dev)
+    pg = p.to(dev).requires_grad_(True)
+    out = m({'x_phy': x.to(dev)}, pg)
+    out['streamflow'].sum().backward()
+    for k in ref:
+        assert_close(out[k], ref[k], RTOL_FLUX, k)
+    assert_close(pg.grad, pc.grad, RTOL_GRAD, 'grad')
+
+
+def test_no_cpu_fallback():
+    import hydrodl2_b200 as hydrodl2
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'dynamic_params': {'Hbv': []}, 'nmul': 2}, device=torch.device('cpu'))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m({'x_phy': torch.zeros(4, 3, 3)}, torch.zeros(4, 3, 26))
