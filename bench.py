@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py — basin-timesteps/sec of the HBV hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one training step of the hot path on one batch of synthetic inputs:
+`Hbv.forward(x_dict, parameters)` (365-day no-grad warm-up + 730-day run, nmul=16, dynamic
+[parBETA, parBETAET], UH routing, BFI) followed by `streamflow.sum().backward()` — the
+BASELINE.json configs[1] workload ("c2": 531 basins x (365 + 730) days per GPU).  Basins shard
+across GPUs with no data-path collective (weak scaling: 531 basins per GPU); the only
+collective is the all-reduce of a shared-parameter gradient.
+
+One JSON line is printed by rank 0.  `value` = device-resident throughput, `e2e` = the same
+step through the public API with pinned HOST buffers (H2D of x_phy + parameters, D2H of
+streamflow + loss + parameter gradient inside the timed region), `roofline` = the dominant
+kernel against the measured HBM peak, `cpu_baseline` = the CPU oracle port (the reference's
+PyTorch arithmetic, oracle/hbv_oracle.py) timed on this box's host cores, `at_scale` = the
+same step on the north-star per-GPU shard (22,500 basins) where the kernels are
+throughput- rather than latency-bound.
+
+`--impl reference` times the CPU oracle port (the reference is pure Python/PyTorch and is not
+shipped to the GPU box; the port is bit-exact against it, tests/test_oracle_golden.py).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'basin-timesteps/sec fwd+bwd (HBV, nmul=16)'
+UNIT = 'basin-timesteps/s'
+NMUL = 16
+DYN = ['parBETA', 'parBETAET']
+WARM_UP, T_MAIN = 365, 730
+WORKLOADS = {
+    # name: basins per GPU
+    'c2': 531,        # BASELINE.json configs[1]
+    'shard': 22500,   # north-star per-GPU shard: 180k basins / 8 GPUs
+}
+SEED = 20261017
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {
+        0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap',
+        0x8: 'hw_slowdown', 0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown',
+        0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting',
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit and name != 'gpu_idle':
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._once()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml unavailable']}
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def make_inputs(B, seed, device=None, pin=False):
+    """Synthetic forcings + raw parameters ~ N(0,1)."""
+    from oracle.hbv_oracle import synthetic_forcing  # input generator only
+    T = WARM_UP + T_MAIN
+    ncol = 13 * NMUL + 2
+    if device is not None and B > 4096:
+        # large shard: generate on the device (same distributions, different stream)
+        g = torch.Generator(device=device).manual_seed(seed)
+        import math
+        d = torch.arange(T, dtype=torch.float32, device=device).view(T, 1)
+        ob = torch.rand(1, B, generator=g, device=device) * 16 - 8
+        season = torch.sin(2 * math.pi * (d - 110) / 365)
+        tmean = 5 + 12 * season + ob + 4 * torch.randn(T, B, generator=g, device=device)
+        prcp = 5 * torch.relu(torch.randn(T, B, generator=g, device=device))
+        pet = torch.relu(2 + 2 * season) + 0.5 * torch.rand(T, B, generator=g, device=device)
+        x = torch.stack([prcp, tmean, pet], dim=-1).contiguous()
+        p = torch.randn(T, B, ncol, generator=g, device=device)
+        return x, p
+    x = synthetic_forcing(T, B, seed=seed)
+    p = torch.randn(T, B, ncol, generator=torch.Generator().manual_seed(seed + 1))
+    if pin:
+        x, p = x.pin_memory(), p.pin_memory()
+    return x, p
+
+
+def model_config():
+    return {'warm_up': WARM_UP, 'dynamic_params': {'Hbv': DYN}, 'nmul': NMUL}
+
+
+# algorithmic bytes per basin-timestep, nmul = 16, n_dyn = 2
+def bytes_fwd(n_dyn=2, n_out=11):
+    return 4 * (3 + n_dyn * NMUL + n_out)
+
+
+def bytes_bwd(n_dyn=2, n_g=1, K=16):
+    return 4 * (3 + 2 * n_dyn * NMUL + n_g) + 5 * NMUL * 4 / K
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_step(x, p, frac=1.0):
+    """One fwd+bwd of the CPU oracle on the first `frac` of the warm-up and of the run."""
+    from oracle import hbv_oracle as O
+    w = max(1, int(round(WARM_UP * frac)))
+    m = max(1, int(round(T_MAIN * frac)))
+    xs = torch.cat([x[:w], x[WARM_UP:WARM_UP + m]])
+    ps = torch.cat([p[:w], p[WARM_UP:WARM_UP + m]]).detach().requires_grad_(True)
+    t0 = time.perf_counter()
+    out, _ = O.forward_packed('hbv', xs, ps, nmul=NMUL, warm_up=w, dynamic_params=DYN)
+    out['streamflow'].sum().backward()
+    dt = time.perf_counter() - t0
+    return dt, x.shape[1] * m
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = WORKLOADS[args.workload] if args.basins is None else args.basins
+    B = min(B, 531)   # bounded sample of the workload's basins
+    x, p = make_inputs(B, SEED)
+    # size the per-step sample so the whole run stays within a few minutes
+    t_probe, _ = cpu_step(x, p, frac=0.05)
+    est_full = t_probe / 0.05
+    budget = 150.0
+    frac = min(1.0, budget / max(1e-9, est_full * (args.steps + args.warmup)))
+    frac = max(frac, 0.02)
+    for _ in range(args.warmup):
+        cpu_step(x, p, frac)
+    tot, units = 0.0, 0
+    for _ in range(args.steps):
+        dt, u = cpu_step(x, p, frac)
+        tot += dt
+        units += u
+    val = units / tot
+    sample = (f'{B} basins x ({int(round(WARM_UP * frac))} warm-up + {int(round(T_MAIN * frac))}) days '
+              f'per step (fraction {frac:.3f} of the c2 time axis), fwd+bwd')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'c2: hbv fwd+bwd, 531 basins x (365 warm-up + 730) days, nmul 16, '
+                               'dynamic [parBETA, parBETAET]', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    from hydrodl2_b200 import _cabi, dist as D, ops
+    import hydrodl2_b200 as hydrodl2
+
+    if not torch.cuda.is_available():
+        print('bench.py: no CUDA device — the B200 arm has no CPU fallback', file=sys.stderr)
+        return 2
+    rank, local, world = D.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f'bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    _cabi.load()
+    Hbv = hydrodl2.load_model('hbv', ver_name='Hbv')
+
+    def build(B, pin):
+        x, p = make_inputs(B, SEED + rank, device=dev, pin=pin)
+        model = Hbv(dict(model_config(), ckpt_interval=args.ckpt), device=dev)
+        return model, x, p
+
+    def train_step(model, x_dev, p_dev):
+        p_dev.grad = None
+        out = model({'x_phy': x_dev}, p_dev)
+        loss = out['streamflow'].sum()
+        loss.backward()
+        # gradient of a bias on the static-parameter row shared by all basins (stands in for
+        # the shared NN weights): the one quantity that needs a cross-GPU reduction
+        gshared = p_dev.grad[-1].sum(dim=0)
+        D.allreduce_shared_grad(gshared)
+        return out, loss, gshared
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        D.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.stop()
+        D.barrier()
+        return D.max_over_ranks(e0.elapsed_time(e1), dev)   # ms, max over ranks
+
+    def kernel_ms(prof):
+        res = {}
+        for name, evs in prof.items():
+            res[name] = sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))
+        return res
+
+    B = WORKLOADS[args.workload] if args.basins is None else args.basins
+    peak, peak_src = measured_peak_gbs()
+
+    # ---------------- device-resident throughput (value) + per-kernel roofline ----------------
+    model, x_host, p_host = build(B, pin=True)
+    x_dev = x_host.to(dev)
+    p_dev = p_host.to(dev).requires_grad_(True)
+    n0 = _cabi.launch_count()
+    train_step(model, x_dev, p_dev)
+    torch.cuda.synchronize(dev)
+    launches_per_step = _cabi.launch_count() - n0
+
+    sampler = ClockSampler(local)
+    ops.PROFILE = {}
+    ms_total = timed(lambda: train_step(model, x_dev, p_dev), args.steps, args.warmup, sampler)
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    torch.cuda.synchronize(dev)
+    # keep only the events of the timed steps (drop warm-up)
+    per_step_calls = {k: len(v) // (args.steps + args.warmup) for k, v in prof.items()}
+    prof = {k: v[args.warmup * per_step_calls[k]:] for k, v in prof.items()}
+    kms = kernel_ms(prof)
+    ms_step = ms_total / args.steps
+    value = world * B * T_MAIN / (ms_step * 1e-3)
+
+    dom = max(kms, key=kms.get)
+    units = B * (T_MAIN if dom != 'hbv_fwd_warmup' else WARM_UP)
+    per_unit = {'hbv_bwd': bytes_bwd(K=args.ckpt), 'hbv_fwd': bytes_fwd(), 'hbv_fwd_warmup': 12.0,
+                'route_fwd': 32.0, 'route_bwd': 24.0}[dom]
+    achieved = per_unit * units / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[dom],
+                'note': 'c2 has 531 basins x 16 = 8,496 lanes (<3% of one B200 wave): the step is '
+                        'latency-bound, see at_scale.roofline for the throughput regime'}
+
+    # ---------------- forward only (inference, no_grad) ----------------
+    def fwd_only():
+        with torch.no_grad():
+            model({'x_phy': x_dev}, p_dev)
+    ms_fwd = timed(fwd_only, args.steps, args.warmup) / args.steps
+    fwd = {'value': world * B * T_MAIN / (ms_fwd * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fwd}
+
+    # ---------------- end to end with host buffers ----------------
+    e2e = None
+    if x_host.is_cuda:   # shard-sized inputs are generated on the device: no host copy to time
+        del x_dev, p_dev, x_host, p_host, model
+        torch.cuda.empty_cache()
+    else:
+        e2e = _e2e(args, dev, world, B, model, x_host, p_host, x_dev, p_dev, train_step, timed)
+        del x_dev, p_dev, x_host, p_host, model
+        torch.cuda.empty_cache()
+
+    # ---------------- north-star per-GPU shard ----------------
+    at_scale = None
+    if not args.no_at_scale and args.workload == 'c2' and args.basins is None:
+        Bs = WORKLOADS['shard']
+        model_s, xs, ps = build(Bs, pin=False)
+        ps.requires_grad_(True)
+        ops.PROFILE = {}
+        s_steps, s_warm = 5, 3
+        ms_s = timed(lambda: train_step(model_s, xs, ps), s_steps, s_warm) / s_steps
+        prof_s = ops.PROFILE
+        ops.PROFILE = None
+        pc = {k: len(v) // (s_steps + s_warm) for k, v in prof_s.items()}
+        kms_s = kernel_ms({k: v[s_warm * pc[k]:] for k, v in prof_s.items()})
+        ms_sf = timed(lambda: _nograd(model_s, xs, ps), s_steps, s_warm) / s_steps
+        a_b = bytes_bwd(K=args.ckpt) * Bs * T_MAIN / (kms_s['hbv_bwd'] * 1e-3) / 1e9
+        a_f = bytes_fwd() * Bs * T_MAIN / (kms_s['hbv_fwd'] * 1e-3) / 1e9
+        at_scale = {
+            'workload': f'hbv fwd+bwd, {Bs} basins/GPU x ({WARM_UP} warm-up + {T_MAIN}) days, nmul 16, D2',
+            'value': world * Bs * T_MAIN / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
+            'fwd_value': world * Bs * T_MAIN / (ms_sf * 1e-3), 'fwd_ms_per_step': ms_sf,
+            'kernel_ms': kms_s,
+            'roofline': {'bound': 'hbm', 'kernel': 'hbv_bwd', 'achieved': a_b, 'peak': peak,
+                         'unit': 'GB/s', 'frac': a_b / peak,
+                         'algorithmic_bytes_per_basin_step': bytes_bwd(K=args.ckpt)},
+            'roofline_fwd': {'bound': 'hbm', 'kernel': 'hbv_fwd', 'achieved': a_f, 'peak': peak,
+                             'unit': 'GB/s', 'frac': a_f / peak,
+                             'algorithmic_bytes_per_basin_step': bytes_fwd()},
+        }
+        del model_s, xs, ps
+        torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        xc, pc_ = make_inputs(min(B, 531), SEED)
+        frac = 1.0 if B <= 531 else 0.5
+        dt, u = cpu_step(xc, pc_, frac)
+        cpu_baseline = {'value': u / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                        'sample': f'{min(B, 531)} basins x ({int(WARM_UP * frac)} warm-up + '
+                                  f'{int(T_MAIN * frac)}) days, fwd+bwd, one step, {dt:.1f} s of CPU work'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': f'{args.workload}: hbv fwd+bwd training step, {B} basins/GPU x '
+                            f'({WARM_UP} warm-up + {T_MAIN}) days, nmul {NMUL}, dynamic {DYN}, '
+                            f'UH routing + BFI, loss = streamflow.sum()',
+                'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': WARM_UP,
+                'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': args.ckpt,
+                'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
+                'l2': 'inputs larger than L2: parameters + gradient = '
+                      f'{2 * (WARM_UP + T_MAIN) * B * (13 * NMUL + 2) * 4 / 1e6:.0f} MB per step vs 126 MB L2',
+            },
+            'clocks': sampler.summary(), 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
+            'gpu_launches_per_step': launches_per_step,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'fwd': fwd, 'kernel_ms': kms,
+            'at_scale': at_scale,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def _e2e(args, dev, world, B, model, x_host, p_host, x_dev, p_dev, train_step, timed):
+    """Same step through the public API with pinned HOST buffers, copies inside the timed region."""
+    g_host = torch.empty_like(p_host).pin_memory()
+    q_host = torch.empty(T_MAIN, B, 1).pin_memory()
+    l_host = torch.empty(()).pin_memory()
+    xd = torch.empty_like(x_dev)
+    pd = torch.empty_like(p_dev.detach()).requires_grad_(True)
+
+    def e2e_step():
+        xd.copy_(x_host, non_blocking=True)
+        with torch.no_grad():
+            pd.copy_(p_host, non_blocking=True)
+        out, loss, _ = train_step(model, xd, pd)
+        q_host.copy_(out['streamflow'], non_blocking=True)
+        l_host.copy_(loss.detach(), non_blocking=True)
+        g_host.copy_(pd.grad, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()   # the caller needs the results on the host
+
+    e2e_steps = max(3, min(args.steps, 20))
+    ms_e2e = timed(e2e_step, e2e_steps, 3) / e2e_steps
+    h2d = x_host.numel() * 4 + p_host.numel() * 4
+    d2h = g_host.numel() * 4 + q_host.numel() * 4 + 4
+    return {'value': world * B * T_MAIN / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'what': 'pinned host x_phy + parameters -> device, Hbv.forward + backward, '
+                    'streamflow + loss + parameter gradient -> pinned host'}
+
+
+def _nograd(model, x, p):
+    with torch.no_grad():
+        return model({'x_phy': x}, p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
+    ap.add_argument('--workload', choices=list(WORKLOADS), default='c2')
+    ap.add_argument('--basins', type=int, default=None, help='override basins per GPU')
+    ap.add_argument('--ckpt', type=int, default=16, choices=[1, 8, 16, 32])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-at-scale', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -45,17 +45,24 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, math: int | None = None) -> str:
+    """Compile every .cu for sm_100a and link the shared library.  Returns its path.
+
+    math=0 builds the precise-math variant (IEEE division, libdevice powf/expf/logf) as
+    ``lib/libhbv_b200_precise.so``; the default library uses the SFU path (hbv_step.cuh)."""
+    out = LIB if math is None else os.path.join(LIBDIR, 'libhbv_b200_precise.so' if math == 0
+                                                else f'libhbv_b200_math{math}.so')
+    if math is None and not force and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = nvcc_path()
     objs = []
     procs = []
+    tag = '' if math is None else f'_m{math}'
+    extra = [] if math is None else [f'-DHBV_MATH={math}']
     for s in SOURCES:
-        o = os.path.join(LIBDIR, s.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, s), '-o', o]
+        o = os.path.join(LIBDIR, s.replace('.cu', f'{tag}.o'))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, '-c', os.path.join(CSRC, s), '-o', o]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')
@@ -63,18 +70,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f'nvcc failed on {s}:\n{out}')
-        if verbose and out:
-            print(out)
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB, *objs]
+            raise RuntimeError(f'nvcc failed on {s}:\n{log}')
+        if verbose and log:
+            print(log)
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', out, *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}')
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv,
+                 math=0 if '--precise' in sys.argv else None)
     print(path)

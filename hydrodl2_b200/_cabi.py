@@ -50,6 +50,7 @@ class HbvBwdIO(C.Structure):
         ('forcing', _fp), ('dyn', _fp), ('sta', _fp), ('drop', _fp), ('attrs', _fp),
         ('muwts', _fp), ('ckpt', _fp), ('gflux', _fp * HBV_MAX_FLUX), ('gstate_out', _fp),
         ('gstate_series', _fp), ('gdyn', _fp), ('gsta', _fp), ('gstate_in', _fp),
+        ('gdyn_zero_fill', C.c_int32), ('reserved_', C.c_int32),
     ]
 
 
@@ -73,7 +74,10 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libhbv_b200.so')
+    # HBV_B200_LIB: load an alternative build of the same ABI (e.g. the HBV_MATH=0 precise-math
+    # build used by scripts/parity_report.py to quantify the SFU-math error)
+    return os.environ.get('HBV_B200_LIB') or os.path.join(
+        os.path.dirname(os.path.abspath(__file__)), 'lib', 'libhbv_b200.so')
 
 
 def load():

@@ -34,6 +34,7 @@ struct BwdPtrs {
     const float* attrs; const float* muwts; const float* ckpt;
     const float* gflux[HBV_MAX_FLUX]; const float* gstate_out; const float* gstate_series;
     float* gdyn; float* gsta; float* gstate_in;
+    int zero_fill;
 };
 
 // value in [0,1] (or raw) -> physical parameter
@@ -50,6 +51,124 @@ __device__ __forceinline__ float descale_grad(const KDesc& d, int i, float raw) 
     }
     return d.span[i];
 }
+
+// value + derivative with one sigmoid evaluation
+__device__ __forceinline__ void descale_both(const KDesc& d, int i, float raw, float& val, float& dval) {
+    if (d.apply_sigmoid) {
+        const float s = sigmoidf_(raw);
+        val = s * d.span[i] + d.lo[i];
+        dval = d.span[i] * s * (1.0f - s);
+    } else {
+        val = raw * d.span[i] + d.lo[i];
+        dval = d.span[i];
+    }
+}
+
+// ---- which parameters are time-varying -----------------------------------------------------
+// DM >= 0: compile-time bit mask (bit i = parameter i is read from row t of `dyn`); requires
+//          no dropout mask.  DM = -1: runtime mask (any set, dropout allowed).
+constexpr int DM_D2 = (1 << HBV_P_BETA) | (1 << HBV_P_BETAET);   // the reference's shipped set
+
+__host__ __device__ constexpr int popc_c(unsigned x) {
+    int n = 0;
+    while (x) { n += (int)(x & 1u); x >>= 1; }
+    return n;
+}
+
+template <int NPAR, int DM>
+struct DynSet {
+    static constexpr bool STATIC = DM >= 0;
+    static constexpr int NDYN = STATIC ? popc_c((unsigned)(DM < 0 ? 0 : DM)) : NPAR;
+    static constexpr int NS = NDYN > 0 ? NDYN : 1;     // raw values carried per prefetched step
+    // steps per prefetch buffer: two buffers (A/B) alternate, so inputs are requested
+    // CL..2*CL steps before they are consumed
+    static constexpr int CL = (NDYN <= 3) ? 2 : 1;
+    __host__ __device__ static constexpr int slot(int i) {
+        return STATIC ? popc_c((unsigned)(DM < 0 ? 0 : DM) & ((1u << i) - 1u)) : i;
+    }
+    __device__ __forceinline__ static bool is_dyn(int i, uint32_t dynmask) {
+        return STATIC ? (((DM < 0 ? 0 : DM) >> i) & 1) : ((dynmask >> i) & 1u);
+    }
+};
+
+// inputs of one time step as loaded (raw, not yet descaled)
+template <int NS>
+struct StepIn { float P, T, PET; float raw[NS]; };
+
+// Resolve every parameter's source for this lane; load + descale the time-invariant ones.
+// Returns the lane's dynamic mask.  dpd / lastmask may be null (forward).
+template <int NPAR, int DM>
+__device__ __forceinline__ uint32_t resolve_params(const KDesc& d, const float* dyn, const float* sta,
+                                                   const uint8_t* drop, int b, int j, float (&p)[NPAR],
+                                                   float* dpd, uint32_t* lastmask) {
+    uint32_t dynmask = 0;
+    const float* dyn_last = dyn + ((int64_t)(d.T - 1) * d.B + b) * d.dyn_ncol + j;
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) {
+        p[i] = 0.f;
+        if (dpd) dpd[i] = 0.f;
+        if (i < d.n_par) {
+            int src = d.src[i];
+            if (DM < 0 && src == HBV_SRC_DYN_T && drop != nullptr && drop[(int64_t)i * d.B + b]) src = HBV_SRC_DYN_LAST;
+            const bool isdyn = (DM >= 0) ? (((DM < 0 ? 0 : DM) >> i) & 1) : (src == HBV_SRC_DYN_T);
+            if (isdyn) {
+                dynmask |= (1u << i);
+            } else {
+                float raw;
+                if (src == HBV_SRC_STA) raw = __ldg(sta + (int64_t)b * d.sta_ncol + d.col[i] + j);
+                else { raw = __ldg(dyn_last + d.col[i]); if (lastmask) *lastmask |= (1u << i); }
+                float v, dv;
+                descale_both(d, i, raw, v, dv);
+                p[i] = v;
+                if (dpd) dpd[i] = dv;
+            }
+        }
+    }
+    return dynmask;
+}
+
+template <int NPAR, int DM>
+__device__ __forceinline__ void load_step(const KDesc& d, const float* fptr, int64_t f_tstride,
+                                          const float* dyn_lane, int64_t dyn_tstride, uint32_t dynmask,
+                                          int t, StepIn<DynSet<NPAR, DM>::NS>& in) {
+    using DS = DynSet<NPAR, DM>;
+    const float* fr = fptr + (int64_t)t * f_tstride;
+    in.P = __ldg(fr + d.i_prcp);
+    in.T = __ldg(fr + d.i_tmean);
+    in.PET = __ldg(fr + d.i_pet);
+    if (DS::STATIC ? (DM != 0) : (dynmask != 0)) {
+        const float* dr = dyn_lane + (int64_t)t * dyn_tstride;
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, dynmask)) in.raw[DS::slot(i)] = __ldg(dr + d.col[i]);
+    }
+}
+
+template <int NPAR, int DM>
+__device__ __forceinline__ void apply_dyn(const KDesc& d, uint32_t dynmask,
+                                          const StepIn<DynSet<NPAR, DM>::NS>& in, float (&p)[NPAR], float* dpd) {
+    using DS = DynSet<NPAR, DM>;
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i)
+        if (DS::is_dyn(i, dynmask)) {
+            if (dpd) { float v, dv; descale_both(d, i, in.raw[DS::slot(i)], v, dv); p[i] = v; dpd[i] = dv; }
+            else p[i] = descale(d, i, in.raw[DS::slot(i)]);
+        }
+}
+
+// host: the runtime dynamic set as a bit mask, or -1 when a dropout mask forces the generic path
+inline int static_dynmask(const KDesc& d, bool has_drop) {
+    if (has_drop) return -1;
+    int m = 0;
+    for (int i = 0; i < d.n_par; ++i) if (d.src[i] == HBV_SRC_DYN_T) m |= (1 << i);
+    return m;
+}
+
+// Compiler-level ordering point.  The prefetch loads of a later step are placed AFTER the point
+// where the current step's inputs are consumed: outstanding loads share the warp's six
+// scoreboard slots, and a wait on a slot waits for every load armed on it — if the new loads were
+// issued first, consuming the old values would stall for a full HBM round trip every step.
+__device__ __forceinline__ void order_point() { asm volatile("" ::: "memory"); }
 
 void set_error(const char* msg);
 void count_launch(int n = 1);

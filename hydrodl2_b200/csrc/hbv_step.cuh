@@ -37,6 +37,7 @@ template <> struct Traits<HBV_VARIANT_HOURLY> {
 // Per-lane constants that do not change over time.
 struct LaneConst {
     float Ac, Elev;     // hbv_2 family attributes
+    float lfexp;        // exp(clamp(-(Ac-2500)/50, -10, 0)): lateral-flux factor for Ac >= 2500
     float nearzero;
     float dt, inv_dt;
 };
@@ -53,7 +54,35 @@ struct Tape {
     float SPg, MWg, SMg, SUZg, SLZg;  // guard-rail inputs (hourly)
 };
 
+// ---- math primitives --------------------------------------------------------------------
+// HBV_MATH = 0: IEEE division, powf/expf/logf (libdevice, ~100 instructions per powf)
+// HBV_MATH = 1: SFU path (default): x^y = ex2(y * lg2(x)), division = x * rcp(y), exp via ex2.
+//   The bases are strictly positive here (SM >= nearzero, FC >= 50, 1 - s >= 0.01); measured
+//   parity against the reference is reported in DESIGN.md §6 (well inside 1e-5 / 1e-4).
+#ifndef HBV_MATH
+#define HBV_MATH 1
+#endif
+
+__device__ __forceinline__ float lg2_approx(float a) {
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+__device__ __forceinline__ float ex2_approx(float a) {
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+__device__ __forceinline__ float rcp_approx(float a) {
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+#if HBV_MATH == 0
 __device__ __forceinline__ float pow_pos(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float flog(float a) { return logf(a); }
+__device__ __forceinline__ float fexp(float a) { return expf(a); }
+#else
+__device__ __forceinline__ float pow_pos(float a, float b) { return ex2_approx(b * lg2_approx(a)); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * rcp_approx(b); }
+__device__ __forceinline__ float flog(float a) { return 0.693147180559945f * lg2_approx(a); }
+__device__ __forceinline__ float fexp(float a) { return ex2_approx(1.442695040888963f * a); }
+#endif
 
 // Forward step.  S = {SNOWPACK, MELTWATER, SM, SUZ, SLZ} updated in place.
 // P and PET are the forcing values as the step uses them (hourly: already / dt).
@@ -100,14 +129,14 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     if constexpr (TR::HOURLY) MW3 = MW2 - tosoil * dt; else MW3 = MW2 - tosoil;
 
     // Soil -----------------------------------------------------------------------------------
-    const float r = SM / p[HBV_P_FC];
+    const float r = fdiv(SM, p[HBV_P_FC]);
     const float sw0 = pow_pos(r, p[HBV_P_BETA]);
     const float sw = fminf(fmaxf(sw0, 0.f), 1.f);
     const float W = RAIN + tosoil;
     float infil = W, IE = 0.f, s_base = 1.f, pw = 0.f, fcap = 0.f, fmin = 0.f;
     float recharge, SM1;
     if constexpr (TR::HOURLY) {  // hbv_2_hourly.py:575-595
-        const float s = fminf(fmaxf(r, 0.f), 1.0f - 0.01f);
+        const float s = fminf(fmaxf(r, 0.f), 0.99f);
         fmin = p[HBV_P_FMIN] * p[HBV_P_F0];
         s_base = 1.0f - s;
         pw = pow_pos(s_base, p[HBV_P_ALPHA]);
@@ -126,7 +155,7 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     float SM2;
     if constexpr (TR::HOURLY) SM2 = SM1 - excess * dt; else SM2 = SM1 - excess;
     const float den = p[HBV_P_LP] * p[HBV_P_FC];
-    const float ef0 = SM2 / den;
+    const float ef0 = fdiv(SM2, den);
     float ef1 = ef0;
     if constexpr (BETAET) ef1 = pow_pos(ef0, p[HBV_P_BETAET]);
     const float ef = fminf(fmaxf(ef1, 0.f), 1.f);
@@ -140,7 +169,7 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     // Capillary rise (hbv_1_1p.py:482-490) -----------------------------------------------------
     float SMf = SM3, SLZa = SLZ, capillary = 0.f, r2 = 0.f, capf = 0.f, c1 = 0.f, SMc = 0.f, SLZc = 0.f;
     if constexpr (TR::CAP) {
-        r2 = SM3 / p[HBV_P_FC];
+        r2 = fdiv(SM3, p[HBV_P_FC]);
         capf = 1.0f - fminf(r2, 1.0f);
         c1 = p[HBV_P_C] * SLZ * capf;
         if constexpr (TR::HOURLY) c1 = c1 * dt;
@@ -179,10 +208,10 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     if constexpr (TR::LAT) {  // hbv_2.py:545-550
         float LF;
         if (c.Ac < 2500.f) {
-            lfarg = (c.Ac - p[HBV_P_AC]) / 1000.f;
+            lfarg = (c.Ac - p[HBV_P_AC]) * 0.001f;
             lfval = fminf(fmaxf(lfarg, -1.f), 1.f);
         } else {
-            lfval = expf(fminf(fmaxf(-(c.Ac - 2500.f) / 50.f, -10.f), 0.f));
+            lfval = c.lfexp;
         }
         LF = lfval * p[HBV_P_RT];
         if constexpr (TR::HOURLY) LF = LF * dt;
@@ -303,7 +332,7 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
         gSLZ_in += gc0 * p[HBV_P_C] * tp.capf;
         const float gcapf = gc0 * p[HBV_P_C] * tp.SLZin;
         const float gr2 = (tp.r2 <= 1.0f) ? -gcapf : 0.f;
-        const float q = gr2 / p[HBV_P_FC];
+        const float q = fdiv(gr2, p[HBV_P_FC]);
         gSM3 += q;
         gp[HBV_P_FC] -= q * tp.r2;
     } else {
@@ -323,11 +352,11 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     const float gef1 = (tp.ef1 >= 0.f && tp.ef1 <= 1.f) ? gef : 0.f;
     float gef0 = gef1;
     if constexpr (BETAET) {
-        gef0 = gef1 * p[HBV_P_BETAET] * tp.ef1 / tp.ef0;
-        gp[HBV_P_BETAET] += gef1 * tp.ef1 * logf(tp.ef0);
+        gef0 = fdiv(gef1 * p[HBV_P_BETAET] * tp.ef1, tp.ef0);
+        gp[HBV_P_BETAET] += gef1 * tp.ef1 * flog(tp.ef0);
     }
     // ef0 = SM2/den ; den = LP*FC
-    const float qe = gef0 / tp.den;
+    const float qe = fdiv(gef0, tp.den);
     gSM2 += qe;
     const float gden = -qe * tp.ef0;
     gp[HBV_P_LP] += gden * p[HBV_P_FC];
@@ -357,17 +386,17 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
         const float gpw = gfcap * (p[HBV_P_F0] - tp.fmin);
         gp[HBV_P_F0] += gfcap * tp.pw + gfmin * p[HBV_P_FMIN];
         gp[HBV_P_FMIN] += gfmin * p[HBV_P_F0];
-        gp[HBV_P_ALPHA] += gpw * tp.pw * logf(tp.s_base);
-        const float gbase = gpw * p[HBV_P_ALPHA] * tp.pw / tp.s_base;
-        gr = (tp.r >= 0.f && tp.r <= 1.0f - 0.01f) ? -gbase : 0.f;
+        gp[HBV_P_ALPHA] += gpw * tp.pw * flog(tp.s_base);
+        const float gbase = fdiv(gpw * p[HBV_P_ALPHA] * tp.pw, tp.s_base);
+        gr = (tp.r >= 0.f && tp.r <= 0.99f) ? -gbase : 0.f;
     } else {
         gW = ginfil;
     }
     // sw = clamp(sw0, 0, 1) ; sw0 = r^BETA ; r = SM/FC
     const float gsw0 = (tp.sw0 >= 0.f && tp.sw0 <= 1.f) ? gsw : 0.f;
-    gr += gsw0 * p[HBV_P_BETA] * tp.sw0 / tp.r;
-    gp[HBV_P_BETA] += gsw0 * tp.sw0 * logf(tp.r);
-    const float qr = gr / p[HBV_P_FC];
+    gr += fdiv(gsw0 * p[HBV_P_BETA] * tp.sw0, tp.r);
+    gp[HBV_P_BETA] += gsw0 * tp.sw0 * flog(tp.r);
+    const float qr = fdiv(gr, p[HBV_P_FC]);
     gSM_in += qr;
     gp[HBV_P_FC] -= qr * tp.r;
     // W = RAIN + tosoil ; MW3 = MW2 - tosoil*dt ; tosoil = max(ts0, 0) ; ts0 = (MW2 - CWH*SP3)/dt
@@ -407,7 +436,20 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     }
 }
 
+__device__ __forceinline__ void init_lane_const(LaneConst& lc, float Ac, float Elev) {
+    lc.Ac = Ac; lc.Elev = Elev;
+    lc.lfexp = expf(fminf(fmaxf(-(Ac - 2500.f) / 50.f, -10.f), 0.f));   // hbv_2.py:547-549
+}
+
 // sigmoid + affine descale (hbv.py:201, core/calc/utils.py:24)
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid (hbv.py:201).  Kept at full float accuracy in both math modes: the threshold
+// temperature enters as T - parTT, a cancellation that amplifies parameter error ~10x.
+__device__ __forceinline__ float sigmoidf_(float x) {
+    const float e = expf(-fminf(fmaxf(x, -80.f), 80.f));
+    const float dn = 1.0f + e;
+    float r = rcp_approx(dn);
+    r = fmaf(r, fmaf(-dn, r, 1.0f), r);   // one Newton step: ~0.5 ulp
+    return r;
+}
 
 }  // namespace hbv

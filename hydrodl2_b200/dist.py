@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing: basins shard, nothing else does.
+
+Every (basin, component) lane of the recurrence and every basin of the UH convolution is
+independent, so the basin axis is partitioned contiguously over the ranks with NO data-path
+collective.  The only exchange in a training step is the all-reduce (sum) of gradients of
+parameters that are *shared* across basins (the parameter network of δMG; in `bench.py` a
+shared per-column bias on the raw parameters) — tiny and latency-bound.
+One process per GPU; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests).
+"""
+
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_basins: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced partition of the basin axis: ranks < n % world get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f'bad rank/world {rank}/{world}')
+    base, rem = divmod(n_basins, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the process group
+    when WORLD_SIZE > 1."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def allreduce_shared_grad(g: torch.Tensor) -> torch.Tensor:
+    """Sum a shared-parameter gradient over ranks (in place); no-op for a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    return g
+
+
+def max_over_ranks(value: float, device) -> float:
+    """Max of a host scalar over ranks (timing: the slowest rank defines the step)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return float(value)
+
+
+def barrier() -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

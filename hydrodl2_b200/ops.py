@@ -21,6 +21,43 @@ from . import _cabi as A
 
 _ROUTED = (A.F_QSIM, A.F_Q0, A.F_Q1, A.F_Q2)
 
+# Optional per-call device timing (bench.py): when PROFILE is a dict, every C-ABI call is
+# bracketed by CUDA events recorded on the stream the kernels are launched on.
+PROFILE = None
+
+# How the dense [T_total, B, ncol] parameter-gradient tensor gets its zeros:
+#   False (default): allocated and memset on a side stream while the forward kernel runs (the
+#                    forward is FP32-issue bound and leaves HBM idle, so the memset is hidden);
+#   True:            K2 writes every element itself (hbv_bwd_io_t.gdyn_zero_fill = 1).
+FUSED_ZERO_FILL = False
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(dev)
+    return _SIDE_STREAMS[key]
+
+
+class _timed:
+    def __init__(self, name, dev):
+        self.name, self.dev = name, dev
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.dev))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream(self.dev))
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
 
 @dataclass
 class RunSpec:
@@ -132,7 +169,8 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
     io.drop, io.attrs, io.muwts = _ptr(drop), _ptr(attrs), None
     io.state_in, io.state_out = _ptr(state_in), _ptr(state_out)
     with torch.cuda.device(forcing.device):
-        A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), _stream(forcing.device)), 'fwd(warm-up)')
+        with _timed('hbv_fwd_warmup', forcing.device):
+            A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), _stream(forcing.device)), 'fwd(warm-up)')
     return state_out
 
 
@@ -158,6 +196,19 @@ class _HbvRun(torch.autograd.Function):
         if not need_grad:
             d.ckpt_interval = 0
 
+        # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
+        gbuf = gev = None
+        if need_grad and dyn is not None and dyn.requires_grad and not FUSED_ZERO_FILL:
+            cur = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            gbuf = torch.empty_like(dyn)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gbuf.zero_()
+                gev = torch.cuda.Event()
+                gev.record(side)
+            gbuf.record_stream(side)
+
         flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
         state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
         series = (torch.empty((5, T, B, nmul), device=dev, dtype=torch.float32)
@@ -171,7 +222,8 @@ class _HbvRun(torch.autograd.Function):
         io.state_series, io.ckpt = _ptr(series), _ptr(ckpt)
         stream = _stream(dev)
         with torch.cuda.device(dev):
-            A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), stream), 'fwd')
+            with _timed('hbv_fwd', dev):
+                A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), stream), 'fwd')
 
             routed = uh = bfi = bfi_ws = None
             rdesc = route_t = None
@@ -189,12 +241,14 @@ class _HbvRun(torch.autograd.Function):
                 if spec.bfi:
                     bfi = torch.empty((B,), device=dev, dtype=torch.float32)
                     bfi_ws = torch.empty((2, nch, B), device=dev, dtype=torch.float32)
-                A.check(lib.hbv_b200_route_fwd(C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(),
-                                               T * B, routed.data_ptr(), T * B, uh.data_ptr(),
-                                               _ptr(bfi), _ptr(bfi_ws), stream), 'route_fwd')
+                with _timed('route_fwd', dev):
+                    A.check(lib.hbv_b200_route_fwd(C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(),
+                                                   T * B, routed.data_ptr(), T * B, uh.data_ptr(),
+                                                   _ptr(bfi), _ptr(bfi_ws), stream), 'route_fwd')
 
         ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
         ctx.has = (dyn is not None, sta is not None)
+        ctx.gbuf, ctx.gev = gbuf, gev
         ctx.save_for_backward(forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in)
         ctx.set_materialize_grads(False)
         outs = [flux[f] for f in range(spec.nflux)]
@@ -222,9 +276,26 @@ class _HbvRun(torch.autograd.Function):
         t_off = ctx.t_off
         stream = _stream(dev)
 
-        gdyn_full = torch.zeros_like(dyn) if dyn is not None else None
+        # The dense [T_total, B, ncol] parameter gradient is part of the contract.  K2 writes
+        # every element of the run's rows itself (fused zero-fill); only the warm-up rows (no
+        # gradient, hbv.py:328) and the non-parameter columns of the last row are zeroed here.
+        gdyn_full = gdyn_run = None
+        zero_fill = 0
+        if dyn is not None:
+            if ctx.gbuf is not None:
+                gdyn_full, ctx.gbuf = ctx.gbuf, None
+                torch.cuda.current_stream(dev).wait_event(ctx.gev)
+            elif FUSED_ZERO_FILL and dyn_ncol <= 32 * nmul:
+                zero_fill = 1
+                gdyn_full = torch.empty_like(dyn)
+                if t_off > 0:
+                    gdyn_full[:t_off].zero_()
+                if spec.n_par * nmul < dyn_ncol:
+                    gdyn_full[dyn.shape[0] - 1, :, spec.n_par * nmul:].zero_()
+            else:
+                gdyn_full = torch.zeros_like(dyn)
+            gdyn_run = gdyn_full[t_off:]
         gsta = torch.zeros_like(sta) if sta is not None else None
-        gdyn_run = gdyn_full[t_off:] if gdyn_full is not None else None
 
         with torch.cuda.device(dev):
             if spec.routing and (any(g is not None for g in g_rout) or g_bfi is not None):
@@ -247,11 +318,17 @@ class _HbvRun(torch.autograd.Function):
                 nch = lib.hbv_b200_route_chunks(T, B)
                 ws = torch.empty((min(spec.lenF, T), nch, B), device=dev, dtype=torch.float32)
                 gb = None if g_bfi is None else g_bfi.contiguous()
-                A.check(lib.hbv_b200_route_bwd(
-                    C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(), T * B, None, T * B,
-                    uh.data_ptr(), _ptr(bfi_ws), g_out.data_ptr(), T * B, mask, _ptr(gb),
-                    g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
+                with _timed('route_bwd', dev):
+                    A.check(lib.hbv_b200_route_bwd(
+                        C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(), T * B, None, T * B,
+                        uh.data_ptr(), _ptr(bfi_ws), g_out.data_ptr(), T * B, mask, _ptr(gb),
+                        g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
                 for s in range(n_r):
+                    # a series without upstream gradient (and no BFI term) has an all-zero
+                    # adjoint plane: do not make K2 read it
+                    live = bool(mask >> s & 1) or (gb is not None and s in (rdesc.bfi_num, rdesc.bfi_den))
+                    if not live:
+                        continue
                     f = _ROUTED[s]
                     g_flux[f] = g_in[s] if g_flux[f] is None else g_flux[f] + g_in[s]
 
@@ -265,9 +342,11 @@ class _HbvRun(torch.autograd.Function):
             gser = None if (g_series is None or not spec.state_series) else g_series.contiguous()
             io.gstate_out, io.gstate_series = _ptr(gs), _ptr(gser)
             io.gdyn, io.gsta = _ptr(gdyn_run), _ptr(gsta)
+            io.gdyn_zero_fill = zero_fill
             gstate_in = torch.empty_like(state_in) if state_in.requires_grad else None
             io.gstate_in = _ptr(gstate_in)
-            A.check(lib.hbv_b200_bwd(C.byref(d), C.byref(io), stream), 'bwd')
+            with _timed('hbv_bwd', dev):
+                A.check(lib.hbv_b200_bwd(C.byref(d), C.byref(io), stream), 'bwd')
         return (None, None, gdyn_full, gsta, gstate_in, None, None, None, None)
 
 

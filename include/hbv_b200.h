@@ -139,11 +139,17 @@ typedef struct hbv_bwd_io {
     const float* gflux[HBV_MAX_FLUX];  /* upstream grads, each [T, B] or NULL */
     const float* gstate_out;           /* [5, B, nmul] or NULL              */
     const float* gstate_series;        /* [5, T, B, nmul] or NULL           */
-    float* gdyn;     /* [T, B, dyn_ncol], ZERO-INITIALISED by the caller: the
-                        kernel writes only the entries that receive gradient
-                        (row t for dynamic parameters, row T-1 for static ones) */
+    float* gdyn;     /* [T, B, dyn_ncol].  gdyn_zero_fill = 0: ZERO-INITIALISED by the
+                        caller, the kernel writes only entries that receive gradient
+                        (row t for dynamic parameters, row T-1 for static ones).
+                        gdyn_zero_fill = 1: uninitialised memory is fine — the kernel
+                        writes EVERY element of rows 0..T-2 (zeros where no gradient
+                        flows) and, in row T-1, every physical-parameter column; row T-1
+                        columns beyond n_par*nmul (routing) are left untouched.          */
     float* gsta;     /* [B, sta_ncol] or NULL                               */
     float* gstate_in;/* [5, B, nmul] or NULL                                */
+    int32_t gdyn_zero_fill;
+    int32_t reserved_;
 } hbv_bwd_io_t;
 
 /* K1: fused forward recurrence + nmul aggregation (hbv.py:363-511). */

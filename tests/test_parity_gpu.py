@@ -78,6 +78,26 @@ def test_streamflow_only_gradient_vs_oracle():
     assert_close(pg.grad, pc.grad, RTOL_GRAD, 'grad')
 
 
+@pytest.mark.parametrize('case', ['hbv_d2', 'hbv_d2_drop_nowarm', 'hbv_1_1p_d14'])
+def test_fused_zero_fill_gradient(case):
+    """K2 writing the whole dense gradient tensor itself (gdyn_zero_fill = 1) into
+    uninitialised memory gives the same gradient as the memset path."""
+    from hydrodl2_b200 import ops
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    ops.FUSED_ZERO_FILL = True
+    try:
+        torch.empty(1 << 22, device=dev).fill_(float('nan'))   # poison the allocator's free blocks
+        m, out, p = _run_packed(g, dev)
+        loss = 0.0
+        for k, c in g['cot'].items():
+            loss = loss + (out[k] * c.to(dev)).sum()
+        loss.backward()
+    finally:
+        ops.FUSED_ZERO_FILL = False
+    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad fused zero-fill')
+
+
 def test_no_cpu_fallback():
     import hydrodl2_b200 as hydrodl2
     M = hydrodl2.load_model('hbv', ver_name='Hbv')
