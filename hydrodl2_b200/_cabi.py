@@ -64,10 +64,21 @@ class HbvRouteDesc(C.Structure):
     ]
 
 
+class HbvPairDesc(C.Structure):
+    _fields_ = [
+        ('abi_version', C.c_int32), ('T', C.c_int32), ('n_pairs', C.c_int32),
+        ('n_units', C.c_int32), ('n_gages', C.c_int32), ('lenF', C.c_int32),
+        ('lag_uh', C.c_int32), ('a_lo', C.c_float), ('a_hi', C.c_float), ('b_lo', C.c_float),
+        ('b_hi', C.c_float), ('tau_lo', C.c_float), ('tau_hi', C.c_float),
+        ('reserved', C.c_int32 * 4),
+    ]
+
+
 EXPORTS = (
     'hbv_b200_fwd', 'hbv_b200_bwd', 'hbv_b200_route_chunks', 'hbv_b200_route_fwd',
     'hbv_b200_route_bwd', 'hbv_b200_abi_version', 'hbv_b200_last_error',
-    'hbv_b200_launch_count',
+    'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
+    'hbv_b200_pair_route_bwd',
 )
 
 _LIB = None
@@ -110,6 +121,12 @@ def load():
     lib.hbv_b200_route_bwd.argtypes = [C.POINTER(HbvRouteDesc), _fp, _fp, C.c_int64, _fp,
                                        C.c_int64, _fp, _fp, _fp, C.c_int64, C.c_uint32, _fp,
                                        _fp, C.c_int64, _fp, _fp, C.c_void_p]
+    lib.hbv_b200_pair_chunks.restype = C.c_int
+    lib.hbv_b200_pair_chunks.argtypes = [C.c_int32]
+    lib.hbv_b200_pair_route_fwd.restype = C.c_int
+    lib.hbv_b200_pair_route_fwd.argtypes = [C.POINTER(HbvPairDesc)] + [_fp] * 9 + [C.c_void_p]
+    lib.hbv_b200_pair_route_bwd.restype = C.c_int
+    lib.hbv_b200_pair_route_bwd.argtypes = [C.POINTER(HbvPairDesc)] + [_fp] * 14 + [C.c_void_p]
     _LIB = lib
     return lib
 

@@ -152,7 +152,8 @@ class SplitHbv(torch.nn.Module):
             ckpt_interval=self.ckpt_interval, routing=routing, route_src='sta',
             route_col=len(sta) * self.nmul,
             route_bounds=tuple(tuple(v) for v in self.routing_parameter_bounds.values()),
-            lenF=self.lenF, n_routed=4, bfi=True, state_series=self.state_series,
+            lenF=self.lenF, n_routed=1 if self._variant == A.VARIANT_HOURLY else 4,
+            bfi=self._variant != A.VARIANT_HOURLY, state_series=self.state_series,
         )
 
     def _draw_drop(self, ngrid: int) -> Optional[torch.Tensor]:
@@ -202,6 +203,10 @@ class SplitHbv(torch.nn.Module):
     def _run(self, x, dyn, sta, current, attrs, drop, routing):
         if self.comprout:
             raise RuntimeError('comprout=True is not supported (it fails in the reference as well)')
+        if routing and self.lenF > 16:
+            raise NotImplementedError(
+                'per-unit UH routing with lenF > 16 (routing=True on the hourly model) is not '
+                'implemented; the hourly model routes through distr_routing (use_distr_routing)')
         spec = self._spec(routing)
         if self.initialize:
             # hbv_2.py:630-632: only the storages are returned

@@ -203,6 +203,46 @@ HBV_API int hbv_b200_route_bwd(const hbv_route_desc_t* desc, const float* route,
                        const float* g_bfi, float* g_in, int64_t gin_stride,
                        float* g_route, float* ws, void* stream);
 
+/*
+ * K4': distributed (gage, unit) pair routing (hbv_2_hourly.py:800-897: distr_routing +
+ * _frac_shift1d).  Pairs are the non-zeros of outlet_topo in row-major order (sorted by gage).
+ *
+ *   par        [n_pairs, 3] in [0,1]: route_a, route_b, route_tau (descaled with the bounds below)
+ *   qs         [T, n_units] unit runoff
+ *   areas      [n_units]
+ *   pair_col   [n_pairs] unit of each pair;  pair_row [n_pairs] gage of each pair
+ *   gage_off   [n_gages + 1] CSR offsets of the pairs of each gage
+ *   inv_denom  [n_gages] 1 / clamp(sum_u topo[g,u] * area[u], 1e-6)
+ *   unit_off   [n_units + 1], unit_perm [n_pairs]: pairs grouped by unit (CSC) for the adjoint
+ *   uh         [min(T,lenF), n_pairs] out: lagged unit hydrographs (kept for the adjoint)
+ *   lag        [T, n_pairs] workspace: per-pair convolved runoff
+ *   out        [T, n_gages] gage streamflow
+ */
+typedef struct hbv_pair_desc {
+    int32_t abi_version;
+    int32_t T, n_pairs, n_units, n_gages, lenF;
+    int32_t lag_uh;                 /* 1: apply the fractional lag (hbv_2_hourly.py:832-833) */
+    float a_lo, a_hi, b_lo, b_hi, tau_lo, tau_hi;
+    int32_t reserved[4];
+} hbv_pair_desc_t;
+
+HBV_API int hbv_b200_pair_chunks(int32_t T);
+
+HBV_API int hbv_b200_pair_route_fwd(const hbv_pair_desc_t* desc, const float* par, const float* qs,
+                                    const float* areas, const int32_t* pair_col,
+                                    const int32_t* gage_off, const float* inv_denom, float* uh,
+                                    float* lag, float* out, void* stream);
+
+/*   g_out [T, n_gages] upstream gradient;  g_lag_ws [T, n_pairs] workspace;
+ *   duh_ws [min(T,lenF), hbv_b200_pair_chunks(T), n_pairs] workspace;
+ *   g_qs [T, n_units] and g_par [n_pairs, 3] are written. */
+HBV_API int hbv_b200_pair_route_bwd(const hbv_pair_desc_t* desc, const float* par, const float* qs,
+                                    const float* areas, const int32_t* pair_col,
+                                    const int32_t* pair_row, const float* inv_denom,
+                                    const int32_t* unit_off, const int32_t* unit_perm,
+                                    const float* uh, const float* g_out, float* g_lag_ws,
+                                    float* duh_ws, float* g_qs, float* g_par, void* stream);
+
 /* misc */
 HBV_API int hbv_b200_abi_version(void);
 HBV_API const char* hbv_b200_last_error(void);

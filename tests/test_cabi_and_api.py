@@ -33,8 +33,9 @@ def test_struct_sizes_match_header():
     import subprocess
     import tempfile
     from hydrodl2_b200 import _cabi
-    code = '#include <stdio.h>\n#include "hbv_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",' \
-           'sizeof(hbv_desc_t),sizeof(hbv_fwd_io_t),sizeof(hbv_bwd_io_t),sizeof(hbv_route_desc_t));return 0;}'
+    code = '#include <stdio.h>\n#include "hbv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+           'sizeof(hbv_desc_t),sizeof(hbv_fwd_io_t),sizeof(hbv_bwd_io_t),sizeof(hbv_route_desc_t),' \
+           'sizeof(hbv_pair_desc_t));return 0;}'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, 't.c')
         open(c, 'w').write(code)
@@ -42,7 +43,8 @@ def test_struct_sizes_match_header():
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_cabi.HbvDesc), ctypes.sizeof(_cabi.HbvFwdIO),
-                     ctypes.sizeof(_cabi.HbvBwdIO), ctypes.sizeof(_cabi.HbvRouteDesc)]
+                     ctypes.sizeof(_cabi.HbvBwdIO), ctypes.sizeof(_cabi.HbvRouteDesc),
+                     ctypes.sizeof(_cabi.HbvPairDesc)]
 
 
 def test_argument_validation_without_gpu():

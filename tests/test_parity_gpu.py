@@ -98,6 +98,61 @@ def test_fused_zero_fill_gradient(case):
     assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad fused zero-fill')
 
 
+SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3']
+SPLIT_CLS = {'hbv_2': 'Hbv_2', 'hbv_2_hourly': 'Hbv_2_hourly'}
+
+
+def _run_split(g, dev, ckpt=16, state_series=True):
+    import hydrodl2_b200 as hydrodl2
+    model = str(g['model'])
+    cls = SPLIT_CLS[model]
+    T, B, nmul, _, seed = (int(v) for v in g['meta'])
+    M = hydrodl2.load_model(model, ver_name=cls)
+    cfg = {'dynamic_params': {cls: [str(s) for s in g['dyn']]}, 'nmul': nmul,
+           'dy_drop': float(g['dy_drop']), 'routing': bool(int(g['routing'])),
+           'ckpt_interval': ckpt, 'state_series': state_series}
+    m = M(cfg, device=dev)
+    p0 = g['p0'].to(dev).requires_grad_(True)
+    p1 = g['p1'].to(dev).requires_grad_(True)
+    params = [p0, p1]
+    xd = {'x_phy': g['x_phy'].to(dev), 'ac_all': g['ac_all'].to(dev), 'elev_all': g['elev_all'].to(dev)}
+    if model == 'hbv_2_hourly':
+        params.append(g['p2'].to(dev).requires_grad_(True))
+        xd['outlet_topo'] = g['outlet_topo'].to(dev)
+        xd['areas'] = g['areas'].to(dev)
+    torch.manual_seed(seed)
+    out = m(xd, params)
+    return m, out, params
+
+
+@pytest.mark.parametrize('case', SPLIT)
+def test_split_forward_matches_reference(case):
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    m, out, _ = _run_split(g, dev)
+    assert set(out.keys()) == set(g['out'].keys())
+    for k, ref in g['out'].items():
+        assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k}')
+    for name, s in zip(m.state_names, m._state_cache):
+        assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name}')
+
+
+@pytest.mark.parametrize('ckpt', [1, 16])
+@pytest.mark.parametrize('case', SPLIT)
+def test_split_gradient_matches_reference(case, ckpt):
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    m, out, params = _run_split(g, dev, ckpt, state_series=(ckpt == 16))
+    loss = 0.0
+    for k, c in g['cot'].items():
+        loss = loss + (out[k] * c.to(dev)).sum()
+    loss.backward()
+    assert_close(params[0].grad, g['grad']['p0'], RTOL_GRAD, f'{case}:grad dyn K={ckpt}')
+    assert_close(params[1].grad, g['grad']['p1'], RTOL_GRAD, f'{case}:grad static K={ckpt}')
+    if len(params) > 2:
+        assert_close(params[2].grad, g['grad']['p2'], RTOL_GRAD, f'{case}:grad distr K={ckpt}')
+
+
 def test_no_cpu_fallback():
     import hydrodl2_b200 as hydrodl2
     M = hydrodl2.load_model('hbv', ver_name='Hbv')
