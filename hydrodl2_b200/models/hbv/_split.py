@@ -175,7 +175,7 @@ class SplitHbv(torch.nn.Module):
         el = x_dict['elev_all'].to(self.device, dtype=torch.float32).reshape(-1)
         return torch.stack([ac, el]).contiguous()
 
-    def _prep(self, x_dict, parameters):
+    def _prep(self, x_dict, parameters, states=None):
         x = x_dict['x_phy'].contiguous()
         self.muwts = x_dict.get('muwts', None)
         ngrid = x.shape[1]
@@ -183,7 +183,9 @@ class SplitHbv(torch.nn.Module):
         sta = parameters[1]
         if dyn is not None and dyn.shape[-1] == 0:
             dyn = None
-        if (not self.states) or (not self.cache_states):
+        if states is not None:
+            current = torch.stack(tuple(states))
+        elif (not self.states) or (not self.cache_states):
             current = torch.stack(self._init_states(ngrid))
         else:
             current = torch.stack(tuple(self.states))
@@ -216,3 +218,44 @@ class SplitHbv(torch.nn.Module):
                                       sta.detach().contiguous(), current, drop=drop, attrs=attrs)
             return {'flux': None, 'routed': None, 'bfi': None, 'state_out': out, 'series': None}
         return hbv_run(spec, x, dyn, sta, current, drop=drop, attrs=attrs, muwts=self.muwts)
+
+    # ------------------------------------------------------------------ seam
+    def _PBM(self, forcing, Ac, Elevation, states, phy_dy_params_dict, phy_static_params_dict,
+             outlet_topo=None, areas=None, distr_params_dict=None):
+        """Reference-compatible seam (hbv_2.py:392-400, hbv_2_hourly.py:451-462): DESCALED
+        parameter dicts in (dynamic [T, B, nmul], static [B, nmul]); returns
+        ``(flux_dict, state_series)``.  The dicts are packed once and run through the same kernels
+        with an identity descale."""
+        names = list(self.parameter_bounds.keys())
+        dyn_names = [n for n in names if n in phy_dy_params_dict]
+        sta_names = [n for n in names if n not in phy_dy_params_dict]
+        dyn = (torch.cat([phy_dy_params_dict[k] for k in dyn_names], dim=-1).contiguous()
+               if dyn_names else None)
+        sta = torch.cat([phy_static_params_dict[k] for k in sta_names], dim=-1).contiguous()
+        keep = (self.dynamic_params, self.dy_drop)
+        self.dynamic_params, self.dy_drop = dyn_names, 0.0
+        try:
+            spec = self._spec(self.routing)
+        finally:
+            self.dynamic_params, self.dy_drop = keep
+        n = len(names)
+        spec.par_lo, spec.par_hi = [0.0] * n, [1.0] * n
+        if spec.routing:
+            ra = self.routing_param_dict['route_a'].view(-1, 1)
+            rb = self.routing_param_dict['route_b'].view(-1, 1)
+            sta = torch.cat([sta, ra, rb], dim=1).contiguous()
+            spec.route_bounds = ((0.0, 1.0), (0.0, 1.0))
+        attrs = torch.stack([Ac.reshape(Ac.shape[0], -1)[:, 0], Elevation.reshape(Elevation.shape[0], -1)[:, 0]])
+        attrs = attrs.to(self.device, dtype=torch.float32).contiguous()
+        current = torch.stack(tuple(states))
+        x = forcing.contiguous()
+        if self.initialize:
+            with torch.no_grad():
+                spec.state_series = False
+                out = hbv_states_only(spec, x, None if dyn is None else dyn.detach(), sta.detach(),
+                                      current, attrs=attrs)
+            return {}, tuple(out[i].unsqueeze(0) for i in range(5))
+        res = hbv_run(spec, x, dyn, sta, current, attrs=attrs, muwts=self.muwts)
+        series = (tuple(res['series'][i] for i in range(5)) if res['series'] is not None
+                  else tuple(res['state_out'][i].unsqueeze(0) for i in range(5)))
+        return self._flux_from_run(res, x, outlet_topo, areas, distr_params_dict), series

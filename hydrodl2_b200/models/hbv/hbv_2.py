@@ -28,6 +28,9 @@ class Hbv_2(SplitHbv):
             return {}
         return self._flux_dict(res, x)
 
+    def _flux_from_run(self, res, x, outlet_topo=None, areas=None, distr_params_dict=None):
+        return self._flux_dict(res, x)
+
     def _flux_dict(self, res, x) -> dict[str, torch.Tensor]:
         flux, routed = res['flux'], res['routed']
         out = {}

@@ -61,14 +61,22 @@ class Hbv_2_hourly(SplitHbv):
             out[name] = distr_params[:, i] * (hi - lo) + lo
         return out
 
-    def forward(self, x_dict: dict[str, torch.Tensor], parameters) -> dict[str, torch.Tensor]:
-        x, dyn, sta, current, ngrid = self._prep(x_dict, parameters)
+    def forward(self, x_dict: dict[str, torch.Tensor], parameters, states=None) -> dict[str, torch.Tensor]:
+        """hbv_2_hourly.py:376-449.  `states` (optional tuple of 5 [B, nmul] tensors) overrides the
+        initial storages — used by Hbv_2_mts, which hands over the daily model's final states."""
+        x, dyn, sta, current, ngrid = self._prep(x_dict, parameters, states)
         attrs = self._attrs(x_dict)
         drop = self._draw_drop(ngrid)
         res = self._run(x, dyn, sta, current, attrs, drop, self.routing)
         self._store_states(res)
         if self.initialize:
             return {}
+        distr = parameters[2] if len(parameters) > 2 else None
+        return self._flux_from_run(res, x, x_dict.get('outlet_topo'), x_dict.get('areas'), distr)
+
+    def _flux_from_run(self, res, x, outlet_topo=None, areas=None, distr=None):
+        """hbv_2_hourly.py:740-796.  `distr`: [n_pairs, 3] in [0, 1], or the reference's descaled
+        dict {'route_a', 'route_b', 'route_tau'} (from `_descale_distr_parameters`)."""
         qs = (res['routed'][0] if res['routed'] is not None else res['flux'][A.F_QSIM])
         out = {'Qs': qs.unsqueeze(-1) * self.dt}
         if not self.warm_up_states:
@@ -76,6 +84,10 @@ class Hbv_2_hourly(SplitHbv):
             out['Qs'] = out['Qs'][self.pred_cutoff:, :, :]
         if self.use_distr_routing:
             from ...routing import distr_routing
+            bounds = tuple(tuple(v) for v in self.distr_parameter_bounds.values())
+            if isinstance(distr, dict):
+                distr = torch.stack([distr[k] for k in self.distr_parameter_bounds.keys()], dim=1)
+                bounds = tuple((0.0, 1.0) for _ in bounds)
             if self.cache_states:   # streaming: keep <= _max_history steps of runoff history
                 self._qs_buffer.append(out['Qs'].detach())
                 if len(self._qs_buffer) > self._max_history:
@@ -83,10 +95,18 @@ class Hbv_2_hourly(SplitHbv):
                 qs_history = torch.cat(self._qs_buffer, dim=0)
             else:
                 qs_history = out['Qs']
-            rout = distr_routing(
-                qs_history, parameters[2], x_dict['outlet_topo'].to(self.device),
-                x_dict['areas'].to(self.device), lenF=self.lenF, lag_uh=self.lag_uh,
-                bounds=tuple(tuple(v) for v in self.distr_parameter_bounds.values()),
-            )
+            rout = distr_routing(qs_history, distr, outlet_topo.to(self.device),
+                                 areas.to(self.device), lenF=self.lenF, lag_uh=self.lag_uh,
+                                 bounds=bounds)
             out['streamflow'] = rout[-1:] if self.cache_states else rout
         return out
+
+    def distr_routing(self, Qs, distr_params_dict, outlet_topo, areas):
+        """Same signature and result as the reference method (hbv_2_hourly.py:800-855):
+        DESCALED pair parameters in, ``{'Qs_rout': [T, n_gages, 1]}`` out."""
+        from ...routing import distr_routing
+        names = list(self.distr_parameter_bounds.keys())
+        par = torch.stack([distr_params_dict[k] for k in names], dim=1)
+        rout = distr_routing(Qs, par, outlet_topo.to(Qs.device), areas.to(Qs.device), lenF=self.lenF,
+                             lag_uh=self.lag_uh, bounds=tuple((0.0, 1.0) for _ in names))
+        return {'Qs_rout': rout}

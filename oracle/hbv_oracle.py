@@ -551,6 +551,36 @@ def forward_split(name, x_dict, parameters, *, nmul=16, dynamic_params=(),
     return out, series
 
 
+def forward_mts(x_dict, parameters, *, nmul=16, low_dynamic=(), high_dynamic=(), nearzero=1e-5,
+                dtype=None):
+    """``Hbv_2_mts._forward`` (hbv_2_mts.py:100-174), un-chunked training path: daily Hbv_2
+    warm-up (states detached) -> identity state transfer -> param_transfer (hbv_2_mts.py:292-341)
+    -> Hbv_2_hourly._PBM without distributed routing.  Returns ({'Qs'}, hourly state series)."""
+    conv = (lambda z: z.to(dtype)) if dtype is not None else (lambda z: z)
+    (lo_dyn, lo_sta), hi = parameters
+    hi_dyn, hi_sta = hi[0], hi[1]
+    xl = {'x_phy': x_dict['x_phy_low_freq'], 'ac_all': x_dict['ac_all'], 'elev_all': x_dict['elev_all']}
+    _, series = forward_split('hbv_2', xl, [lo_dyn, lo_sta], nmul=nmul, dynamic_params=low_dynamic,
+                              nearzero=nearzero, dtype=dtype)
+    states = tuple(s[-1].detach() for s in series)
+    vl, vh = variant('hbv_2', low_dynamic), variant('hbv_2_hourly', high_dynamic)
+    hi_names = [n for n in vh.bounds if n not in high_dynamic]
+    lo_names = [n for n in vl.bounds if n not in low_dynamic]
+    lo3 = conv(lo_sta)[:, :len(lo_names) * nmul].view(-1, len(lo_names), nmul)
+    hi3 = conv(hi_sta)[:, :len(hi_names) * nmul].view(-1, len(hi_names), nmul)
+    extra = [i for i, n in enumerate(hi_names) if n not in lo_names]
+    merged = torch.cat([lo3, hi3[:, extra]], dim=1)
+    x = conv(x_dict['x_phy_high_freq'])
+    T, B = x.shape[0], x.shape[1]
+    dyn01 = conv(hi_dyn).view(T, B, len(high_dynamic), nmul)
+    dyn, stat = descale_split(vh, dyn01, merged, list(high_dynamic), 0.0)
+    Ac = conv(x_dict['ac_all']).unsqueeze(-1).repeat(1, nmul)
+    Elev = conv(x_dict['elev_all']).unsqueeze(-1).repeat(1, nmul)
+    out, _, hs = run_pbm(vh, x, states, dyn, stat, Ac=Ac, Elev=Elev, nmul=nmul, nearzero=nearzero,
+                         routing=False, keep_state_series=True)
+    return out, hs
+
+
 # --------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md §8 d2) — shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------

@@ -130,6 +130,43 @@ def split_case(hydrodl2, case, model, cls, dyn, T, B, nmul, dy_drop, seed, routi
          **({'p2': params[2]} if hourly else {}), **extra)
 
 
+def mts_case(hydrodl2, case, T_low, T_high, B, nmul, seed):
+    M = hydrodl2.load_model('hbv_2_mts', ver_name='Hbv_2_mts')
+    dyn = ['parBETA', 'parK0', 'parBETAET']
+    lo_cfg = {'dynamic_params': {'Hbv_2': dyn}, 'nmul': nmul, 'cache_states': True}
+    hi_cfg = {'dynamic_params': {'Hbv_2_hourly': dyn}, 'nmul': nmul,
+              'train_spatial_chunk_size': 10 ** 6, 'simulate_spatial_chunk_size': 10 ** 6,
+              'simulate_temporal_chunk_size': 10 ** 6, 'train_warmup': 0}
+    m = M(lo_cfg, hi_cfg, device=torch.device('cpu'))
+    g = torch.Generator().manual_seed(seed + 1)
+    xl = synthetic_forcing(T_low, B, seed=seed)
+    xh = synthetic_forcing(T_high, B, seed=seed + 5, hourly=True)
+    lo = m.low_freq_model
+    hi = m.high_freq_model
+    lo_dyn = torch.rand(T_low, B, lo.learnable_param_count1, generator=g).requires_grad_(True)
+    lo_sta = torch.rand(B, lo.learnable_param_count2, generator=g).requires_grad_(True)
+    hi_dyn = torch.rand(T_high, B, hi.learnable_param_count1, generator=g).requires_grad_(True)
+    hi_sta = torch.rand(B, hi.learnable_param_count2, generator=g).requires_grad_(True)
+    topo = torch.zeros(2, B)
+    topo[0, :B // 2] = 1
+    topo[1, B // 2:] = 1
+    areas = torch.rand(B, generator=g) * 99 + 1
+    hi_distr = torch.rand(int(topo.sum()), 3, generator=g)
+    xd = {'x_phy_low_freq': xl, 'x_phy_high_freq': xh, 'ac_all': torch.rand(B, generator=g) * 5000,
+          'elev_all': torch.rand(B, generator=g) * 3500, 'outlet_topo': topo, 'areas': areas}
+    torch.manual_seed(seed + 2)
+    out = m(xd, ([lo_dyn, lo_sta], [hi_dyn, hi_sta, hi_distr]))
+    loss, cots = cotangent(out, seed + 3)
+    loss.backward()
+    zero = torch.zeros(1)
+    save(case, x_low=xl, x_high=xh, ac_all=xd['ac_all'], elev_all=xd['elev_all'], outlet_topo=topo,
+         areas=areas, lo_dyn=lo_dyn, lo_sta=lo_sta, hi_dyn=hi_dyn, hi_sta=hi_sta, hi_distr=hi_distr,
+         out=out, cot=cots,
+         grad={'lo_dyn': lo_dyn.grad if lo_dyn.grad is not None else zero,
+               'lo_sta': lo_sta.grad, 'hi_dyn': hi_dyn.grad, 'hi_sta': hi_sta.grad},
+         meta=np.array([T_low, T_high, B, nmul, seed + 2]), dyn=np.array(dyn, dtype='U16'))
+
+
 def main():
     hydrodl2 = import_reference()
     D2 = ['parBETA', 'parBETAET']
@@ -148,6 +185,7 @@ def main():
                64, 5, 4, 0.3, 650, routing=True)
     split_case(hydrodl2, 'hbv_2_hourly_d3', 'hbv_2_hourly', 'Hbv_2_hourly',
                ['parBETA', 'parK0', 'parBETAET'], 120, 6, 16, 0.0, 700)
+    mts_case(hydrodl2, 'hbv_2_mts_train', 40, 96, 6, 4, 800)
 
 
 if __name__ == '__main__':

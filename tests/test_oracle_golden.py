@@ -69,6 +69,28 @@ def test_split_forward_and_grad(case):
         assert_close(params[2].grad, g['grad']['p2'], 1e-6, f'{case}:grad p2')
 
 
+def _mts_inputs(g, dev='cpu'):
+    xd = {'x_phy_low_freq': g['x_low'].to(dev), 'x_phy_high_freq': g['x_high'].to(dev),
+          'ac_all': g['ac_all'].to(dev), 'elev_all': g['elev_all'].to(dev),
+          'outlet_topo': g['outlet_topo'].to(dev), 'areas': g['areas'].to(dev)}
+    p = {k: g[k].to(dev).clone().requires_grad_(True) for k in ('lo_dyn', 'lo_sta', 'hi_dyn', 'hi_sta')}
+    params = ([p['lo_dyn'], p['lo_sta']], [p['hi_dyn'], p['hi_sta'], g['hi_distr'].to(dev)])
+    return xd, p, params
+
+
+def test_mts_forward_and_grad():
+    g = load_golden('hbv_2_mts_train')
+    nmul = int(g['meta'][3])
+    dyn = [str(s) for s in g['dyn']]
+    xd, p, params = _mts_inputs(g)
+    out, _ = O.forward_mts(xd, params, nmul=nmul, low_dynamic=dyn, high_dynamic=dyn)
+    assert_close(out['Qs'], g['out']['Qs'], TIGHT, 'mts:Qs')
+    (out['Qs'] * g['cot']['Qs']).sum().backward()
+    assert p['lo_dyn'].grad is None                      # warm-up states are detached
+    for k in ('lo_sta', 'hi_dyn', 'hi_sta'):
+        assert_close(p[k].grad, g['grad'][k], 1e-6, f'mts:grad {k}')
+
+
 def test_float64_arbiter_is_close_to_float32():
     g = load_golden('hbv_d2')
     out64, _, _ = _packed(g, dtype=torch.float64)

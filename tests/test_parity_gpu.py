@@ -153,6 +153,61 @@ def test_split_gradient_matches_reference(case, ckpt):
         assert_close(params[2].grad, g['grad']['p2'], RTOL_GRAD, f'{case}:grad distr K={ckpt}')
 
 
+def test_mts_matches_reference():
+    """Hbv_2_mts training path: daily warm-up -> state hand-over -> hourly run (golden from the
+    reference's own Hbv_2_mts.forward)."""
+    import hydrodl2_b200 as hydrodl2
+    from test_oracle_golden import _mts_inputs
+    dev = torch.device('cuda:0')
+    g = load_golden('hbv_2_mts_train')
+    nmul = int(g['meta'][3])
+    dyn = [str(s) for s in g['dyn']]
+    M = hydrodl2.load_model('hbv_2_mts', ver_name='Hbv_2_mts')
+    lo_cfg = {'dynamic_params': {'Hbv_2': dyn}, 'nmul': nmul, 'cache_states': True}
+    hi_cfg = {'dynamic_params': {'Hbv_2_hourly': dyn}, 'nmul': nmul,
+              'train_spatial_chunk_size': 10 ** 6, 'simulate_spatial_chunk_size': 10 ** 6,
+              'simulate_temporal_chunk_size': 10 ** 6, 'train_warmup': 0}
+    m = M(lo_cfg, hi_cfg, device=dev)
+    xd, p, params = _mts_inputs(g, dev)
+    out = m(xd, params)
+    assert set(out.keys()) == {'Qs'}
+    assert_close(out['Qs'], g['out']['Qs'], RTOL_FLUX, 'mts:Qs')
+    (out['Qs'] * g['cot']['Qs'].to(dev)).sum().backward()
+    assert p['lo_dyn'].grad is None or float(p['lo_dyn'].grad.abs().max()) == 0.0
+    for k in ('lo_sta', 'hi_dyn', 'hi_sta'):
+        assert_close(p[k].grad, g['grad'][k], RTOL_GRAD, f'mts:grad {k}')
+
+
+def test_mts_chunked_simulation_equals_unchunked():
+    """Spatial + temporal chunking (hbv_2_mts.py:204-279; broken in the reference) gives the same
+    runoff as the un-chunked run and the same routed flow as one un-chunked routing call."""
+    import hydrodl2_b200 as hydrodl2
+    from hydrodl2_b200.routing import distr_routing
+    from test_oracle_golden import _mts_inputs
+    dev = torch.device('cuda:0')
+    g = load_golden('hbv_2_mts_train')
+    nmul = int(g['meta'][3])
+    dyn = [str(s) for s in g['dyn']]
+    M = hydrodl2.load_model('hbv_2_mts', ver_name='Hbv_2_mts')
+    lo_cfg = {'dynamic_params': {'Hbv_2': dyn}, 'nmul': nmul, 'cache_states': True}
+
+    def run(spatial, temporal, simulate):
+        hi_cfg = {'dynamic_params': {'Hbv_2_hourly': dyn}, 'nmul': nmul,
+                  'train_spatial_chunk_size': spatial, 'simulate_spatial_chunk_size': spatial,
+                  'simulate_temporal_chunk_size': temporal, 'train_warmup': 0}
+        m = M(lo_cfg, hi_cfg, device=dev)
+        m.set_mode(simulate)
+        xd, _, params = _mts_inputs(g, dev)
+        with torch.no_grad():
+            return m(xd, params), xd, params
+
+    full, xd, params = run(10 ** 6, 10 ** 6, False)
+    chunked, _, _ = run(4, 10 ** 6, True)
+    assert_close(chunked['Qs'], full['Qs'], 1e-6, 'chunked Qs')
+    ref_rout = distr_routing(full['Qs'], params[1][2], xd['outlet_topo'], xd['areas'])
+    assert_close(chunked['streamflow'], ref_rout, 1e-6, 'chunked streamflow')
+
+
 def test_no_cpu_fallback():
     import hydrodl2_b200 as hydrodl2
     M = hydrodl2.load_model('hbv', ver_name='Hbv')
