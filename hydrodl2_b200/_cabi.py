@@ -12,9 +12,9 @@ import os
 
 HBV_MAX_PAR = 20
 HBV_MAX_FLUX = 12
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-VARIANT_HBV, VARIANT_HBV11P, VARIANT_HBV2, VARIANT_HOURLY = 0, 1, 2, 3
+VARIANT_HBV, VARIANT_HBV11P, VARIANT_HBV2, VARIANT_HOURLY, VARIANT_ADJ = 0, 1, 2, 3, 4
 SRC_DYN_T, SRC_DYN_LAST, SRC_STA = 0, 1, 2
 
 # flux slots (HBV_F_*)
@@ -33,7 +33,8 @@ class HbvDesc(C.Structure):
         ('sta_ncol', C.c_int32), ('par_src', C.c_int32 * HBV_MAX_PAR),
         ('par_col', C.c_int32 * HBV_MAX_PAR), ('par_lo', C.c_float * HBV_MAX_PAR),
         ('par_hi', C.c_float * HBV_MAX_PAR), ('nearzero', C.c_float), ('dt', C.c_float),
-        ('ckpt_interval', C.c_int32), ('muwts_t_stride', C.c_int32), ('reserved', C.c_int32 * 6),
+        ('ckpt_interval', C.c_int32), ('muwts_t_stride', C.c_int32), ('adj_max_updates', C.c_int32),
+        ('adj_tol', C.c_float), ('reserved', C.c_int32 * 4),
     ]
 
 
@@ -51,6 +52,20 @@ class HbvBwdIO(C.Structure):
         ('muwts', _fp), ('ckpt', _fp), ('gflux', _fp * HBV_MAX_FLUX), ('gstate_out', _fp),
         ('gstate_series', _fp), ('gdyn', _fp), ('gsta', _fp), ('gstate_in', _fp),
         ('gdyn_zero_fill', C.c_int32), ('reserved_', C.c_int32),
+    ]
+
+
+class HbvAdjFwdIO(C.Structure):
+    _fields_ = [
+        ('forcing', _fp), ('dyn', _fp), ('drop', _fp), ('state_in', _fp), ('state_out', _fp),
+        ('qsim', _fp), ('ysol', _fp), ('stats', _fp),
+    ]
+
+
+class HbvAdjBwdIO(C.Structure):
+    _fields_ = [
+        ('forcing', _fp), ('dyn', _fp), ('drop', _fp), ('ysol', _fp), ('gqsim', _fp),
+        ('gstate_out', _fp), ('gdyn', _fp), ('gstate_in', _fp),
     ]
 
 
@@ -78,7 +93,7 @@ EXPORTS = (
     'hbv_b200_fwd', 'hbv_b200_bwd', 'hbv_b200_route_chunks', 'hbv_b200_route_fwd',
     'hbv_b200_route_bwd', 'hbv_b200_abi_version', 'hbv_b200_last_error',
     'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
-    'hbv_b200_pair_route_bwd',
+    'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd',
 )
 
 _LIB = None
@@ -112,6 +127,10 @@ def load():
     lib.hbv_b200_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvFwdIO), C.c_void_p]
     lib.hbv_b200_bwd.restype = C.c_int
     lib.hbv_b200_bwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvBwdIO), C.c_void_p]
+    lib.hbv_b200_adj_fwd.restype = C.c_int
+    lib.hbv_b200_adj_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjFwdIO), C.c_void_p]
+    lib.hbv_b200_adj_bwd.restype = C.c_int
+    lib.hbv_b200_adj_bwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjBwdIO), C.c_void_p]
     lib.hbv_b200_route_chunks.restype = C.c_int
     lib.hbv_b200_route_chunks.argtypes = [C.c_int32, C.c_int32]
     lib.hbv_b200_route_fwd.restype = C.c_int

@@ -16,6 +16,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int fwd_dispatch(const hbv_desc_t* desc, const hbv_fwd_io_t* io, cudaStream_t st);
 int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st);
+int adj_fwd_dispatch(const hbv_desc_t* desc, const hbv_adj_fwd_io_t* io, cudaStream_t st);
+int adj_bwd_dispatch(const hbv_desc_t* desc, const hbv_adj_bwd_io_t* io, cudaStream_t st);
 
 static int expected_npar(int variant, int betaet) {
     switch (variant) {
@@ -23,6 +25,7 @@ static int expected_npar(int variant, int betaet) {
         case HBV_VARIANT_HBV11P: return 14;
         case HBV_VARIANT_HBV2: return 16;
         case HBV_VARIANT_HOURLY: return 19;
+        case HBV_VARIANT_ADJ: return betaet ? 13 : 12;
     }
     return -1;
 }
@@ -79,6 +82,7 @@ int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
 
 int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {
     if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (desc->variant == HBV_VARIANT_ADJ) { hbv::set_error("HBV_VARIANT_ADJ runs through hbv_b200_adj_fwd"); return HBV_E_VARIANT; }
     if (!io->forcing || !io->state_in) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
     if (desc->variant >= HBV_VARIANT_HBV2 && !io->attrs) { hbv::set_error("attrs (Ac, Elevation) required"); return HBV_E_NULL; }
     for (int i = 0; i < desc->n_par && i < HBV_MAX_PAR; ++i)
@@ -89,11 +93,26 @@ int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {
 
 int hbv_b200_bwd(const hbv_desc_t* desc, const hbv_bwd_io_t* io, void* stream) {
     if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (desc->variant == HBV_VARIANT_ADJ) { hbv::set_error("HBV_VARIANT_ADJ runs through hbv_b200_adj_bwd"); return HBV_E_VARIANT; }
     if (!io->forcing || !io->ckpt) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
     if (desc->variant >= HBV_VARIANT_HBV2 && !io->attrs) { hbv::set_error("attrs (Ac, Elevation) required"); return HBV_E_NULL; }
     for (int i = 0; i < desc->n_par && i < HBV_MAX_PAR; ++i)
         if (desc->par_src[i] == HBV_SRC_STA ? (!io->sta || !io->gsta) : (!io->dyn || !io->gdyn)) { hbv::set_error("parameter tensor + gradient required"); return HBV_E_NULL; }
     return hbv::bwd_dispatch(desc, io, (cudaStream_t)stream);
+}
+
+int hbv_b200_adj_fwd(const hbv_desc_t* desc, const hbv_adj_fwd_io_t* io, void* stream) {
+    if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (desc->variant != HBV_VARIANT_ADJ) { hbv::set_error("hbv_b200_adj_fwd needs HBV_VARIANT_ADJ"); return HBV_E_VARIANT; }
+    if (!io->forcing || !io->dyn || !io->state_in) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
+    return hbv::adj_fwd_dispatch(desc, io, (cudaStream_t)stream);
+}
+
+int hbv_b200_adj_bwd(const hbv_desc_t* desc, const hbv_adj_bwd_io_t* io, void* stream) {
+    if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
+    if (desc->variant != HBV_VARIANT_ADJ) { hbv::set_error("hbv_b200_adj_bwd needs HBV_VARIANT_ADJ"); return HBV_E_VARIANT; }
+    if (!io->forcing || !io->dyn || !io->ysol || !io->gdyn) { hbv::set_error("null input pointer"); return HBV_E_NULL; }
+    return hbv::adj_bwd_dispatch(desc, io, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -378,3 +378,140 @@ def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, m
         'state_out': outs[nf + n_r + 1],
         'series': outs[nf + n_r + 2] if spec.state_series else None,
     }
+
+
+# ----------------------------------------------------------------------------------------------
+# K3: implicit HBV (`HbvAdj`, models/hbv/hbv_adj.py)
+# ----------------------------------------------------------------------------------------------
+class _HbvAdjRun(torch.autograd.Function):
+    """Differentiable warm-up + run + routing of the implicit scheme (hbv_adj.py:227-330).
+
+    forward : K3 (warm-up rows, all static) -> K3 (run rows) -> K4 (gamma UH, one series)
+    backward: K4^T -> K3 adjoint (run) -> K3 adjoint (warm-up); one dense gradient tensor for
+              `parameters`, written in place by the kernels."""
+
+    @staticmethod
+    def forward(ctx, spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop, warm_up, newton):
+        lib = A.load()
+        dev = forcing.device
+        Tt, B, nvar = forcing.shape
+        nmul, ncol = spec.nmul, dyn.shape[-1]
+        T = Tt - warm_up
+        tol, maxu = newton
+        need_grad = dyn.requires_grad or state_in.requires_grad
+        stream = _stream(dev)
+        stats = torch.zeros(2, dtype=torch.int32, device=dev)
+
+        def desc_of(sp, nT):
+            d = make_desc(sp, nT, B, nvar, ncol, 0)
+            d.ckpt_interval = 0
+            d.adj_tol, d.adj_max_updates = float(tol), int(maxu)
+            return d
+
+        ysol_w = state_w = None
+        cur = state_in
+        with torch.cuda.device(dev):
+            if warm_up > 0:
+                ysol_w = torch.empty((warm_up, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
+                state_w = torch.empty_like(state_in)
+                io = A.HbvAdjFwdIO()
+                io.forcing, io.dyn, io.drop = _ptr(forcing), _ptr(dyn), None
+                io.state_in, io.state_out, io.qsim = _ptr(cur), _ptr(state_w), None
+                io.ysol, io.stats = _ptr(ysol_w), _ptr(stats)
+                with _timed('hbv_adj_fwd_warmup', dev):
+                    A.check(lib.hbv_b200_adj_fwd(C.byref(desc_of(spec_w, warm_up)), C.byref(io), stream), 'adj_fwd(warm-up)')
+                cur = state_w
+            ysol = torch.empty((T, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
+            qsim = torch.empty((T, B), device=dev, dtype=torch.float32)
+            state_out = torch.empty_like(state_in)
+            io = A.HbvAdjFwdIO()
+            io.forcing, io.dyn, io.drop = _ptr(forcing[warm_up:]), _ptr(dyn[warm_up:]), _ptr(drop)
+            io.state_in, io.state_out, io.qsim = _ptr(cur), _ptr(state_out), _ptr(qsim)
+            io.ysol, io.stats = _ptr(ysol), _ptr(stats)
+            with _timed('hbv_adj_fwd', dev):
+                A.check(lib.hbv_b200_adj_fwd(C.byref(desc_of(spec, T)), C.byref(io), stream), 'adj_fwd')
+
+            routed = uh = None
+            if spec.routing:
+                route_t = dyn[Tt - 1, :, spec.route_col:]
+                rdesc = make_route_desc(spec, T, B, ncol)
+                routed = torch.empty((1, T, B), device=dev, dtype=torch.float32)
+                uh = torch.empty((min(spec.lenF, T), B), device=dev, dtype=torch.float32)
+                with _timed('route_fwd', dev):
+                    A.check(lib.hbv_b200_route_fwd(C.byref(rdesc), route_t.data_ptr(), qsim.data_ptr(), T * B,
+                                                   routed.data_ptr(), T * B, uh.data_ptr(), None, None,
+                                                   stream), 'route_fwd')
+        ctx.specs, ctx.dims, ctx.newton = (spec_w, spec), (Tt, T, B, nvar, ncol, warm_up), newton
+        ctx.save_for_backward(forcing, dyn, drop, state_in, ysol_w, ysol, qsim, uh)
+        ctx.set_materialize_grads(False)
+        return qsim, (routed[0] if routed is not None else qsim.new_zeros(())), state_out, stats
+
+    @staticmethod
+    def backward(ctx, g_q, g_rout, g_state, _g_stats):
+        lib = A.load()
+        spec_w, spec = ctx.specs
+        forcing, dyn, drop, state_in, ysol_w, ysol, qsim, uh = ctx.saved_tensors
+        Tt, T, B, nvar, ncol, warm_up = ctx.dims
+        tol, maxu = ctx.newton
+        dev = forcing.device
+        stream = _stream(dev)
+        if ysol is None:
+            raise RuntimeError('hydrodl2_b200: backward called but no input required grad')
+        gdyn = torch.zeros_like(dyn)
+
+        def desc_of(sp, nT):
+            d = make_desc(sp, nT, B, nvar, ncol, 0)
+            d.ckpt_interval = 0
+            d.adj_tol, d.adj_max_updates = float(tol), int(maxu)
+            return d
+
+        with torch.cuda.device(dev):
+            gq = None if g_q is None else g_q.contiguous()
+            if spec.routing and g_rout is not None:
+                route_t = dyn[Tt - 1, :, spec.route_col:]
+                g_route = gdyn[Tt - 1, :, spec.route_col:]
+                rdesc = make_route_desc(spec, T, B, ncol)
+                nch = lib.hbv_b200_route_chunks(T, B)
+                ws = torch.empty((min(spec.lenF, T), nch, B), device=dev, dtype=torch.float32)
+                g_in = torch.empty((1, T, B), device=dev, dtype=torch.float32)
+                g_out = g_rout.contiguous().view(1, T, B)
+                with _timed('route_bwd', dev):
+                    A.check(lib.hbv_b200_route_bwd(
+                        C.byref(rdesc), route_t.data_ptr(), qsim.data_ptr(), T * B, None, T * B,
+                        uh.data_ptr(), None, g_out.data_ptr(), T * B, 1, None,
+                        g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
+                gq = g_in[0] if gq is None else gq + g_in[0]
+            need_gin = warm_up > 0 or state_in.requires_grad
+            gmid = torch.empty_like(state_in) if need_gin else None
+            io = A.HbvAdjBwdIO()
+            io.forcing, io.dyn, io.drop = _ptr(forcing[warm_up:]), _ptr(dyn[warm_up:]), _ptr(drop)
+            io.ysol, io.gqsim = _ptr(ysol), _ptr(gq)
+            io.gstate_out = None if g_state is None else _ptr(g_state.contiguous())
+            io.gdyn, io.gstate_in = _ptr(gdyn[warm_up:]), _ptr(gmid)
+            with _timed('hbv_adj_bwd', dev):
+                A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec, T)), C.byref(io), stream), 'adj_bwd')
+            gstate_in = gmid
+            if warm_up > 0:
+                gstate_in = torch.empty_like(state_in) if state_in.requires_grad else None
+                io = A.HbvAdjBwdIO()
+                io.forcing, io.dyn, io.drop = _ptr(forcing), _ptr(dyn), None
+                io.ysol, io.gqsim, io.gstate_out = _ptr(ysol_w), None, _ptr(gmid)
+                io.gdyn, io.gstate_in = _ptr(gdyn), _ptr(gstate_in)
+                with _timed('hbv_adj_bwd_warmup', dev):
+                    A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec_w, warm_up)), C.byref(io), stream), 'adj_bwd(warm-up)')
+        return (None, None, None, gdyn, gstate_in if state_in.requires_grad else None, None, None, None)
+
+
+def hbv_adj_run(spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop=None, warm_up: int = 0,
+                tol: float = 1e-3, max_updates: int = 8):
+    """Implicit-scheme run.  forcing [T_total, B, nvar], dyn [T_total, B, ncol] raw packed
+    parameters, state_in [5, B, nmul].  Rows [:warm_up] are the (differentiable) warm-up with
+    static parameters taken from row warm_up-1 (hbv_adj.py:257-274).
+    Returns dict(qsim [T,B], routed [T,B] or None, state_out, stats int32[2])."""
+    _check_cuda(forcing, 'x_phy')
+    _check_cuda(dyn, 'parameters')
+    qsim, routed, state_out, stats = _HbvAdjRun.apply(
+        spec_w, spec, forcing.contiguous(), dyn.contiguous(), state_in.contiguous(), drop,
+        int(warm_up), (tol, max_updates))
+    return {'qsim': qsim, 'routed': routed if spec.routing else None, 'state_out': state_out,
+            'stats': stats}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HBV_B200_ABI_VERSION 1
+#define HBV_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HBV_API __attribute__((visibility("default")))
@@ -51,7 +51,8 @@ enum {
     HBV_VARIANT_HBV = 0,      /* models/hbv/hbv.py:423-505            */
     HBV_VARIANT_HBV11P = 1,   /* models/hbv/hbv_1_1p.py:422-516       */
     HBV_VARIANT_HBV2 = 2,     /* models/hbv/hbv_2.py:464-575          */
-    HBV_VARIANT_HOURLY = 3    /* models/hbv/hbv_2_hourly.py:527-675   */
+    HBV_VARIANT_HOURLY = 3,   /* models/hbv/hbv_2_hourly.py:527-675   */
+    HBV_VARIANT_ADJ = 4       /* models/hbv/hbv_adj.py:341-498 (implicit scheme; hbv_b200_adj_* only) */
 };
 
 /* physical parameter slots — the order of `parameter_bounds`
@@ -108,7 +109,11 @@ typedef struct hbv_desc {
     float dt;                      /* 1 (daily) or 1/24 (hbv_2_hourly.py:58) */
     int32_t ckpt_interval;         /* K: state checkpoint every K steps (0 = none) */
     int32_t muwts_t_stride;        /* elements between time rows of muwts (0 = time-invariant) */
-    int32_t reserved[6];
+    int32_t adj_max_updates;       /* HBV_VARIANT_ADJ: Newton updates per step (0 = default 8;
+                                      the reference allows 4, hbv_adj.py:518,544) */
+    float adj_tol;                 /* HBV_VARIANT_ADJ: ||G||_inf stopping tolerance (0 = default
+                                      1e-3, the reference's gtol, hbv_adj.py:519) */
+    int32_t reserved[4];
 } hbv_desc_t;
 
 /* Forward I/O.  NULL output pointers are skipped. */
@@ -157,6 +162,46 @@ HBV_API int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* s
 
 /* K2: checkpointed adjoint of K1. */
 HBV_API int hbv_b200_bwd(const hbv_desc_t* desc, const hbv_bwd_io_t* io, void* stream);
+
+/*
+ * K3: implicit (backward-Euler) HBV, `HbvAdj` (models/hbv/hbv_adj.py).
+ *
+ * hbv_b200_adj_fwd replaces the per-step NewtonSolve.apply loop (hbv_adj.py:689-712 calling
+ * :504-615: batchJacobian + torch.linalg.solve + three host syncs per iteration) and the flux
+ * read-out + nmul mean (:309-317) by one launch: each (basin, component) lane solves
+ * G(x) = (x - xt)/dt - f(x, p_t, t) = 0 by Newton with the analytic block-triangular Jacobian,
+ * stopping per lane (||G||_inf <= adj_tol, then one polishing update, <= adj_max_updates).
+ * hbv_b200_adj_bwd is the adjoint the reference intends at hbv_adj.py:620-633
+ * (lambda = (dG/dx)^-T dL/dx; dL/dp = -lambda^T dG/dp; dL/dxt = -lambda^T dG/dxt) with
+ * analytic dG/dp in place of core/calc/fdj.py:46-92.
+ * desc->variant must be HBV_VARIANT_ADJ, n_par 12 or 13 (betaet), parameters packed
+ * (HBV_SRC_DYN_T / HBV_SRC_DYN_LAST), dt = 1.
+ */
+typedef struct hbv_adj_fwd_io {
+    const float* forcing;    /* [T, B, nvar]                                   */
+    const float* dyn;        /* [T, B, dyn_ncol] raw packed parameters         */
+    const uint8_t* drop;     /* [n_par, B] or NULL                             */
+    const float* state_in;   /* [5, B, nmul]  (hbv_adj.py:254: zeros)          */
+    float* state_out;        /* [5, B, nmul] or NULL                           */
+    float* qsim;             /* [T, B] nmul-mean of (q0+q1+q2)*dt or NULL      */
+    float* ysol;             /* [T, 5, B, nmul] end-of-step states or NULL (required by bwd) */
+    int32_t* stats;          /* [2] or NULL: max updates used (atomicMax), lane-steps that hit
+                                adj_max_updates unconverged (atomicAdd); caller zeroes it */
+} hbv_adj_fwd_io_t;
+
+typedef struct hbv_adj_bwd_io {
+    const float* forcing;
+    const float* dyn;
+    const uint8_t* drop;
+    const float* ysol;         /* from the forward call                         */
+    const float* gqsim;        /* [T, B] or NULL                                */
+    const float* gstate_out;   /* [5, B, nmul] or NULL                          */
+    float* gdyn;               /* [T, B, dyn_ncol], ZERO-INITIALISED by the caller */
+    float* gstate_in;          /* [5, B, nmul] or NULL                          */
+} hbv_adj_bwd_io_t;
+
+HBV_API int hbv_b200_adj_fwd(const hbv_desc_t* desc, const hbv_adj_fwd_io_t* io, void* stream);
+HBV_API int hbv_b200_adj_bwd(const hbv_desc_t* desc, const hbv_adj_bwd_io_t* io, void* stream);
 
 /*
  * K4: gamma unit hydrograph + causal convolution + BFI

@@ -1,0 +1,70 @@
+"""GPU parity of K3 (implicit HBV, csrc/hbv_adj.cu) through the HbvAdj drop-in class against
+the float64 oracle restatement of hbv_adj.py (oracle/hbv_adj_oracle.py, same per-lane Newton
+rule).  hbv_adj has no runnable reference: parity here is against the restatement (unpinned,
+DESIGN.md §3).  Tolerances: max-norm relative 1e-5 flow, 1e-4 parameter gradient."""
+
+import pytest
+import torch
+
+from conftest import RTOL_FLUX, RTOL_GRAD, assert_close
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, T, B, nmul, warm_up, dynamic, n_par
+    ('static', 120, 9, 4, 0, [], 12),
+    ('d2_warm', 150, 7, 16, 40, ['parBETA', 'parBETAET'], 13),
+    ('d2_nowarm', 100, 33, 8, 0, ['parBETA', 'parBETAET'], 13),
+    ('all_dynamic', 90, 5, 4, 20, ['parBETA', 'parFC', 'parK0', 'parK1', 'parK2', 'parLP', 'parPERC',
+                                   'parUZL', 'parTT', 'parCFMAX', 'parCFR', 'parCWH', 'parBETAET'], 13),
+    ('d1_twelve', 80, 6, 2, 10, ['parK1'], 12),
+]
+
+
+def _run(case, routing=True):
+    from oracle import hbv_adj_oracle as AO
+    from oracle import hbv_oracle as O
+    import hydrodl2_b200 as hydrodl2
+    name, T, B, nmul, warm, dyn, n_par = case
+    dev = torch.device('cuda:0')
+    x = O.synthetic_forcing(T, B, seed=21)
+    gen = torch.Generator().manual_seed(22)
+    p = torch.randn(T, B, n_par * nmul + 2, generator=gen)
+    cot = torch.randn(T - warm, B, 1, generator=gen)
+    p64 = p.double().requires_grad_(True)
+    ref = AO.forward_adj(x.double(), p64, nmul=nmul, warm_up=warm, dynamic_params=dyn, routing=routing)
+    (ref['flow_sim'] * cot.double()).sum().backward()
+    M = hydrodl2.load_model('hbv_adj', ver_name='HbvAdj')
+    m = M({'warm_up': warm, 'dynamic_params': {'HbvAdj': dyn}, 'nmul': nmul, 'routing': routing}, device=dev)
+    pg = p.to(dev).requires_grad_(True)
+    out = m({'x_phy': x.to(dev)}, pg)
+    (out['flow_sim'] * cot.to(dev)).sum().backward()
+    return m, out, pg, ref, p64
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_adj_flow_and_gradient(case):
+    m, out, pg, ref, p64 = _run(case)
+    assert_close(out['flow_sim'], ref['flow_sim'], RTOL_FLUX, f'{case[0]}:flow_sim')
+    assert_close(pg.grad, p64.grad, RTOL_GRAD, f'{case[0]}:grad')
+    stats = m.newton_stats.cpu().tolist()
+    assert 1 <= stats[0] <= m.newton_max_updates and stats[1] == 0, stats
+
+
+def test_adj_no_routing():
+    case = CASES[1]
+    m, out, pg, ref, p64 = _run(case, routing=False)
+    assert_close(out['flow_sim'], ref['flow_sim'], RTOL_FLUX, 'flow_sim (no routing)')
+    assert_close(pg.grad, p64.grad, RTOL_GRAD, 'grad (no routing)')
+
+
+def test_adj_attributes_and_errors():
+    import hydrodl2_b200 as hydrodl2
+    M = hydrodl2.load_model('hbv_adj', ver_name='HbvAdj')
+    m = M({'dynamic_params': {'HbvAdj': ['parBETAET']}, 'nmul': 16}, device=torch.device('cuda:0'))
+    assert m.learnable_param_count == 13 * 16 + 2
+    assert list(m.routing_parameter_bounds) == ['rout_a', 'rout_b']
+    with pytest.raises(KeyError):
+        M({'nmul': 4}, device=torch.device('cuda:0'))
+    with pytest.raises(RuntimeError):
+        m({'x_phy': torch.zeros(4, 2, 3)}, torch.zeros(4, 2, 210))   # CPU tensors: no CPU path
