@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(RB)
 uh_conv_kernel(const RDesc d, const float* __restrict__ uh, const float* __restrict__ x,
                int64_t x_stride, float* __restrict__ y, int64_t y_stride,
                float* __restrict__ bfi_ws) {
-    const int b = blockIdx.x * RB + threadIdx.x;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (b >= d.B) return;
     const int ts = c * d.tch;
@@ -71,7 +71,8 @@ uh_conv_kernel(const RDesc d, const float* __restrict__ uh, const float* __restr
 #pragma unroll
     for (int k = 0; k < MAXM; ++k) u[k] = (k < d.M) ? __ldg(uh + (int64_t)k * d.B + b) : 0.f;
 
-    for (int s = 0; s < d.nser; ++s) {
+    {
+        const int s = blockIdx.z;     // one series per grid plane
         const float* xs = x + s * x_stride + b;
         float* ys = y + s * y_stride + b;
         float win[MAXM - 1 + MAXM];   // win[i] = x[tb - (MAXM-1) + i]
@@ -109,9 +110,10 @@ __global__ void bfi_kernel(const RDesc d, const float* __restrict__ bfi_ws, floa
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= d.B) return;
     float num = 0.f, den = 0.f;
+#pragma unroll 8
     for (int c = 0; c < d.nchunk; ++c) {
-        num += bfi_ws[((int64_t)0 * d.nchunk + c) * d.B + b];
-        den += bfi_ws[((int64_t)1 * d.nchunk + c) * d.B + b];
+        num += __ldg(bfi_ws + ((int64_t)0 * d.nchunk + c) * d.B + b);
+        den += __ldg(bfi_ws + ((int64_t)1 * d.nchunk + c) * d.B + b);
     }
     bfi[b] = 100.f * (num / (den + d.nearzero));
 }
@@ -124,7 +126,7 @@ uh_conv_bwd_kernel(const RDesc d, const float* __restrict__ uh, const float* __r
                    const float* __restrict__ g_out, int64_t g_stride, uint32_t g_mask,
                    const float* __restrict__ g_bfi, float* __restrict__ g_in, int64_t gin_stride,
                    float* __restrict__ ws) {
-    const int b = blockIdx.x * RB + threadIdx.x;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (b >= d.B) return;
     const int ts = c * d.tch;
@@ -199,31 +201,48 @@ uh_conv_bwd_kernel(const RDesc d, const float* __restrict__ uh, const float* __r
         if (k < d.M) ws[((int64_t)k * d.nchunk + c) * d.B + b] = dU[k];
 }
 
-// reduce dU partials over chunks, push through the normalised gamma pdf to (route_a, route_b)
-__global__ void uh_param_bwd_kernel(const RDesc d, const float* __restrict__ route,
-                                    const float* __restrict__ uh, const float* __restrict__ ws,
-                                    float* __restrict__ g_route) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= d.B) return;
+// reduce dU partials over chunks, push through the normalised gamma pdf to (route_a, route_b).
+// 16 threads per basin (one per tap): the chunk sums are independent loads, the five per-basin
+// moments are reduced with shuffles inside the 16-lane group.
+__global__ void __launch_bounds__(128)
+uh_param_bwd_kernel(const RDesc d, const float* __restrict__ route,
+                    const float* __restrict__ uh, const float* __restrict__ ws,
+                    float* __restrict__ g_route) {
+    const int k = threadIdx.x & (MAXM - 1);
+    const int b_raw = blockIdx.x * (blockDim.x / MAXM) + threadIdx.x / MAXM;
+    const int b = min(b_raw, d.B - 1);
+    float g = 0.f, u = 0.f;
+    if (k < d.M) {
+        const float* w = ws + (int64_t)k * d.nchunk * d.B + b;
+#pragma unroll 8
+        for (int c = 0; c < d.nchunk; ++c) g += __ldg(w + (int64_t)c * d.B);
+        u = __ldg(uh + (int64_t)k * d.B + b);
+    }
+    const float t = (float)k + 0.5f;
+    const float L = logf(t);
+    float mL = u * L, mT = u * t;     // sum_j u_j ln t_j, sum_j u_j t_j
+    float sL = g * u * L, sT = g * u * t, s0 = g * u;
+#pragma unroll
+    for (int o = MAXM / 2; o > 0; o >>= 1) {
+        mL += __shfl_xor_sync(0xffffffffu, mL, o);
+        mT += __shfl_xor_sync(0xffffffffu, mT, o);
+        sL += __shfl_xor_sync(0xffffffffu, sL, o);
+        sT += __shfl_xor_sync(0xffffffffu, sT, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    }
+    if (k != 0 || b_raw >= d.B) return;
     float aa, th, da_draw, db_draw;
     route_ab(d, route, b, aa, th, da_draw, db_draw);
-    float mL = 0.f, mT = 0.f;     // sum_j u_j ln t_j, sum_j u_j t_j
-    float sL = 0.f, sT = 0.f, s0 = 0.f;
-    for (int k = 0; k < d.M; ++k) {
-        float g = 0.f;
-        for (int c = 0; c < d.nchunk; ++c) g += ws[((int64_t)k * d.nchunk + c) * d.B + b];
-        const float u = uh[(int64_t)k * d.B + b];
-        const float t = (float)k + 0.5f;
-        const float L = logf(t);
-        mL += u * L; mT += u * t;
-        sL += g * u * L; sT += g * u * t; s0 += g * u;
-    }
     // du_k/daa = u_k (L_k - mL);  du_k/dth = u_k (t_k - mT) / th^2
     const float gaa = sL - s0 * mL;
     const float gth = (sT - s0 * mT) / (th * th);
     g_route[(int64_t)b * d.route_stride] = gaa * da_draw;
     g_route[(int64_t)b * d.route_stride + 1] = gth * db_draw;
 }
+
+// threads (= basins) per CTA of the conv kernels: small CTAs for small B so the (basin-block,
+// chunk) grid still covers the SMs
+static int route_block(int B) { return B >= 8192 ? RB : (B >= 2048 ? 64 : 32); }
 
 static int make_rdesc(const hbv_route_desc_t* r, RDesc& d) {
     if (!r) { set_error("null route desc"); return HBV_E_NULL; }
@@ -247,9 +266,11 @@ using namespace hbv;
 
 extern "C" int hbv_b200_route_chunks(int32_t T, int32_t B) {
     if (T <= 0 || B <= 0) return 1;
-    const int blocks_b = (B + RB - 1) / RB;
-    int want = (2 * 148 + blocks_b - 1) / blocks_b;
-    int maxc = (T + 31) / 32;
+    // one thread per (basin, time chunk): enough chunks to fill the 148 SMs (~1.5k threads
+    // each), but chunks of >= 32 steps so the lenF-1 halo re-read stays small
+    const long long target = 148LL * 1536;
+    int want = (int)((target + B - 1) / B);
+    int maxc = T / 32;
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
     // chunk length is rounded up to a multiple of MAXM: recompute the chunk count it implies
@@ -268,8 +289,9 @@ extern "C" int hbv_b200_route_fwd(const hbv_route_desc_t* desc, const float* rou
     if (!route || !q_in || !q_out || !uh || (bfi && !bfi_ws)) { set_error("null pointer"); return HBV_E_NULL; }
     cudaStream_t st = (cudaStream_t)stream;
     uh_weights_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d, route, uh);
-    dim3 grid((d.B + RB - 1) / RB, d.nchunk);
-    uh_conv_kernel<<<grid, RB, 0, st>>>(d, uh, q_in, q_stride, q_out, out_stride, bfi ? bfi_ws : nullptr);
+    const int rb = route_block(d.B);
+    dim3 grid((d.B + rb - 1) / rb, d.nchunk, d.nser);
+    uh_conv_kernel<<<grid, rb, 0, st>>>(d, uh, q_in, q_stride, q_out, out_stride, bfi ? bfi_ws : nullptr);
     count_launch(2);
     if (bfi) { bfi_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d, bfi_ws, bfi); count_launch(); }
     cudaError_t e = cudaGetLastError();
@@ -291,10 +313,12 @@ extern "C" int hbv_b200_route_bwd(const hbv_route_desc_t* desc, const float* rou
         set_error("null pointer"); return HBV_E_NULL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((d.B + RB - 1) / RB, d.nchunk);
-    uh_conv_bwd_kernel<<<grid, RB, 0, st>>>(d, uh, q_in, q_stride, bfi_ws, g_out, g_stride, g_out_mask,
+    const int rb = route_block(d.B);
+    dim3 grid((d.B + rb - 1) / rb, d.nchunk);
+    uh_conv_bwd_kernel<<<grid, rb, 0, st>>>(d, uh, q_in, q_stride, bfi_ws, g_out, g_stride, g_out_mask,
                                             g_bfi, g_in, gin_stride, ws);
-    uh_param_bwd_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(d, route, uh, ws, g_route);
+    const int bpb = 128 / MAXM;
+    uh_param_bwd_kernel<<<(d.B + bpb - 1) / bpb, 128, 0, st>>>(d, route, uh, ws, g_route);
     count_launch(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) set_error(cudaGetErrorString(e));
