@@ -1,23 +1,24 @@
 #!/usr/bin/env python
 """bench.py — basin-timesteps/sec of the HBV hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one training step of the hot path on one batch of synthetic inputs:
-`Hbv.forward(x_dict, parameters)` (365-day no-grad warm-up + 730-day run, nmul=16, dynamic
-[parBETA, parBETAET], UH routing, BFI) followed by `streamflow.sum().backward()` — the
-BASELINE.json configs[1] workload ("c2": 531 basins x (365 + 730) days per GPU).  Basins shard
-across GPUs with no data-path collective (weak scaling: 531 basins per GPU); the only
-collective is the all-reduce of a shared-parameter gradient.
+`Model.forward(x_dict, parameters)` (no-grad warm-up + run, nmul=16, dynamic parameters, UH
+routing, BFI) followed by `streamflow.sum().backward()`.  The bench line is BASELINE.json
+configs[1] ("c2": hbv, 531 basins x (365 + 730) days per GPU, dynamic [parBETA, parBETAET]).
+Basins shard across GPUs with no data-path collective (weak scaling: 531 basins per GPU); the
+only collective is the all-reduce of a shared-parameter gradient.
 
 One JSON line is printed by rank 0.  `value` = device-resident throughput, `e2e` = the same
 step through the public API with pinned HOST buffers (H2D of x_phy + parameters, D2H of
 streamflow + loss + parameter gradient inside the timed region), `roofline` = the dominant
 kernel against the measured HBM peak, `cpu_baseline` = the CPU oracle port (the reference's
-PyTorch arithmetic, oracle/hbv_oracle.py) timed on this box's host cores, `at_scale` = the
-same step on the north-star per-GPU shard (22,500 basins) where the kernels are
-throughput- rather than latency-bound.
+PyTorch arithmetic, oracle/hbv_oracle.py) timed on this box's host cores.  `at_scale` repeats the
+device-resident measurement on the north-star per-GPU shards, where the kernels are throughput-
+rather than latency-bound: "shard" (same model, 22,500 basins) and "c3" (BASELINE configs[2]:
+hbv_1_1p with all 14 parameters dynamic, 22,500 basins x 730 days — the HBM-bound case).
 
 `--impl reference` times the CPU oracle port (the reference is pure Python/PyTorch and is not
 shipped to the GPU box; the port is bit-exact against it, tests/test_oracle_golden.py).
@@ -27,6 +28,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -41,12 +43,19 @@ import torch  # noqa: E402
 METRIC = 'basin-timesteps/sec fwd+bwd (HBV, nmul=16)'
 UNIT = 'basin-timesteps/s'
 NMUL = 16
-DYN = ['parBETA', 'parBETAET']
-WARM_UP, T_MAIN = 365, 730
+D2 = ['parBETA', 'parBETAET']
+D14 = ['parBETA', 'parFC', 'parK0', 'parK1', 'parK2', 'parLP', 'parPERC', 'parUZL', 'parTT',
+       'parCFMAX', 'parCFR', 'parCWH', 'parBETAET', 'parC']
 WORKLOADS = {
-    # name: basins per GPU
-    'c2': 531,        # BASELINE.json configs[1]
-    'shard': 22500,   # north-star per-GPU shard: 180k basins / 8 GPUs
+    # BASELINE.json configs[1]: the bench line
+    'c2': dict(model='hbv', cls='Hbv', dyn=D2, n_par=13, nflux=11, warm_up=365, T=730, B=531,
+               label='c2: hbv fwd+bwd training step'),
+    # north-star per-GPU shard (180k basins / 8 GPUs) of the same model: FP32-issue bound
+    'shard': dict(model='hbv', cls='Hbv', dyn=D2, n_par=13, nflux=11, warm_up=365, T=730, B=22500,
+                  label='shard: hbv fwd+bwd at the north-star per-GPU basin count'),
+    # BASELINE.json configs[2], one GPU's share: hbv_1_1p, all 14 parameters dynamic: HBM bound
+    'c3': dict(model='hbv_1_1p', cls='Hbv_1_1p', dyn=D14, n_par=14, nflux=12, warm_up=0, T=730,
+               B=22500, label='c3: hbv_1_1p fwd+bwd, all 14 parameters dynamic, 180k basins / 8 GPUs'),
 }
 SEED = 20261017
 
@@ -122,15 +131,14 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
-def make_inputs(B, seed, device=None, pin=False):
+def make_inputs(wl, B, seed, device=None, pin=False):
     """Synthetic forcings + raw parameters ~ N(0,1)."""
     from oracle.hbv_oracle import synthetic_forcing  # input generator only
-    T = WARM_UP + T_MAIN
-    ncol = 13 * NMUL + 2
+    T = wl['warm_up'] + wl['T']
+    ncol = wl['n_par'] * NMUL + 2
     if device is not None and B > 4096:
         # large shard: generate on the device (same distributions, different stream)
         g = torch.Generator(device=device).manual_seed(seed)
-        import math
         d = torch.arange(T, dtype=torch.float32, device=device).view(T, 1)
         ob = torch.rand(1, B, generator=g, device=device) * 16 - 8
         season = torch.sin(2 * math.pi * (d - 110) / 365)
@@ -138,7 +146,11 @@ def make_inputs(B, seed, device=None, pin=False):
         prcp = 5 * torch.relu(torch.randn(T, B, generator=g, device=device))
         pet = torch.relu(2 + 2 * season) + 0.5 * torch.rand(T, B, generator=g, device=device)
         x = torch.stack([prcp, tmean, pet], dim=-1).contiguous()
-        p = torch.randn(T, B, ncol, generator=g, device=device)
+        del tmean, prcp, pet
+        p = torch.empty(T, B, ncol, device=device)
+        tb = max(1, T // 8)
+        for t0 in range(0, T, tb):      # in slabs: randn needs no second full-size temporary
+            p[t0:t0 + tb].normal_(generator=g)
         return x, p
     x = synthetic_forcing(T, B, seed=seed)
     p = torch.randn(T, B, ncol, generator=torch.Generator().manual_seed(seed + 1))
@@ -147,68 +159,85 @@ def make_inputs(B, seed, device=None, pin=False):
     return x, p
 
 
-def model_config():
-    return {'warm_up': WARM_UP, 'dynamic_params': {'Hbv': DYN}, 'nmul': NMUL}
+def model_config(wl):
+    return {'warm_up': wl['warm_up'], 'dynamic_params': {wl['cls']: wl['dyn']}, 'nmul': NMUL}
 
 
-# algorithmic bytes per basin-timestep, nmul = 16, n_dyn = 2
-def bytes_fwd(n_dyn=2, n_out=11):
-    return 4 * (3 + n_dyn * NMUL + n_out)
+# algorithmic bytes per basin-timestep, nmul = 16:
+# every contract input read once, every output written once
+def bytes_fwd(wl, K=16):
+    # forcings + dynamic parameters read, flux planes written, state checkpoint every K steps
+    return 4 * (3 + len(wl['dyn']) * NMUL + wl['nflux']) + 5 * NMUL * 4 / K
 
 
-def bytes_bwd(n_dyn=2, n_g=1, K=16):
-    return 4 * (3 + 2 * n_dyn * NMUL + n_g) + 5 * NMUL * 4 / K
+def bytes_bwd(wl, K=16, n_g=1):
+    # forcings + dynamic parameters + n_g upstream series read, dynamic gradients written,
+    # checkpoints read
+    return 4 * (3 + 2 * len(wl['dyn']) * NMUL + n_g) + 5 * NMUL * 4 / K
+
+
+def per_unit_bytes(wl, K):
+    return {'hbv_bwd': bytes_bwd(wl, K), 'hbv_fwd': bytes_fwd(wl, K), 'hbv_fwd_warmup': 12.0,
+            'route_fwd': 32.0,    # 4 series read + 4 routed series written
+            'route_bwd': 12.0}    # streamflow-only loss: read g, read x, write g_in (1 series)
+
+
+def describe(wl, B):
+    return (f"{wl['label']}, {B} basins/GPU x ({wl['warm_up']} warm-up + {wl['T']}) days, nmul {NMUL}, "
+            f"{len(wl['dyn'])} dynamic parameters {wl['dyn'] if len(wl['dyn']) <= 3 else '(all)'}, "
+            f"UH routing + BFI, loss = streamflow.sum()")
 
 
 # ----------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_step(x, p, frac=1.0):
+def cpu_step(wl, x, p, frac=1.0):
     """One fwd+bwd of the CPU oracle on the first `frac` of the warm-up and of the run."""
     from oracle import hbv_oracle as O
-    w = max(1, int(round(WARM_UP * frac)))
-    m = max(1, int(round(T_MAIN * frac)))
-    xs = torch.cat([x[:w], x[WARM_UP:WARM_UP + m]])
-    ps = torch.cat([p[:w], p[WARM_UP:WARM_UP + m]]).detach().requires_grad_(True)
+    W, Tm = wl['warm_up'], wl['T']
+    w = max(1, int(round(W * frac))) if W else 0
+    m = max(1, int(round(Tm * frac)))
+    xs = torch.cat([x[:w], x[W:W + m]])
+    ps = torch.cat([p[:w], p[W:W + m]]).detach().requires_grad_(True)
     t0 = time.perf_counter()
-    out, _ = O.forward_packed('hbv', xs, ps, nmul=NMUL, warm_up=w, dynamic_params=DYN)
+    out, _ = O.forward_packed(wl['model'], xs, ps, nmul=NMUL, warm_up=w, dynamic_params=wl['dyn'])
     out['streamflow'].sum().backward()
     dt = time.perf_counter() - t0
-    return dt, x.shape[1] * m
+    return dt, x.shape[1] * m, (w, m)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = WORKLOADS[args.workload] if args.basins is None else args.basins
-    B = min(B, 531)   # bounded sample of the workload's basins
-    x, p = make_inputs(B, SEED)
+    B = wl['B'] if args.basins is None else args.basins
+    Bs = min(B, 531)   # bounded sample of the workload's basins
+    x, p = make_inputs(wl, Bs, SEED)
     # size the per-step sample so the whole run stays within a few minutes
-    t_probe, _ = cpu_step(x, p, frac=0.05)
+    t_probe, _, _ = cpu_step(wl, x, p, frac=0.05)
     est_full = t_probe / 0.05
     budget = 150.0
     frac = min(1.0, budget / max(1e-9, est_full * (args.steps + args.warmup)))
     frac = max(frac, 0.02)
     for _ in range(args.warmup):
-        cpu_step(x, p, frac)
-    tot, units = 0.0, 0
+        cpu_step(wl, x, p, frac)
+    tot, units, wm = 0.0, 0, (0, 0)
     for _ in range(args.steps):
-        dt, u = cpu_step(x, p, frac)
+        dt, u, wm = cpu_step(wl, x, p, frac)
         tot += dt
         units += u
     val = units / tot
-    sample = (f'{B} basins x ({int(round(WARM_UP * frac))} warm-up + {int(round(T_MAIN * frac))}) days '
-              f'per step (fraction {frac:.3f} of the c2 time axis), fwd+bwd')
+    sample = (f'{Bs} basins x ({wm[0]} warm-up + {wm[1]}) days per step (fraction {frac:.3f} of the '
+              f'{args.workload} time axis), fwd+bwd')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'c2: hbv fwd+bwd, 531 basins x (365 warm-up + 730) days, nmul 16, '
-                               'dynamic [parBETA, parBETAET]', 'sample': sample},
+        'config': {'workload': describe(wl, B), 'sample': sample},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -233,11 +262,12 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     _cabi.load()
-    Hbv = hydrodl2.load_model('hbv', ver_name='Hbv')
+    peak, peak_src = measured_peak_gbs()
 
-    def build(B, pin):
-        x, p = make_inputs(B, SEED + rank, device=dev, pin=pin)
-        model = Hbv(dict(model_config(), ckpt_interval=args.ckpt), device=dev)
+    def build(wl, B, pin):
+        Model = hydrodl2.load_model(wl['model'], ver_name=wl['cls'])
+        x, p = make_inputs(wl, B, SEED + rank, device=dev, pin=pin)
+        model = Model(dict(model_config(wl), ckpt_interval=args.ckpt), device=dev)
         return model, x, p
 
     def train_step(model, x_dev, p_dev):
@@ -250,6 +280,10 @@ def run_b200(args):
         gshared = p_dev.grad[-1].sum(dim=0)
         D.allreduce_shared_grad(gshared)
         return out, loss, gshared
+
+    def fwd_only(model, x, p):
+        with torch.no_grad():
+            return model({'x_phy': x}, p)
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -270,17 +304,39 @@ def run_b200(args):
         D.barrier()
         return D.max_over_ranks(e0.elapsed_time(e1), dev)   # ms, max over ranks
 
-    def kernel_ms(prof):
-        res = {}
+    def timed_with_kernels(fn, steps, warmup, sampler=None):
+        """-> (ms per step, {kernel group: mean ms per call over the timed steps})."""
+        ops.PROFILE = {}
+        ms = timed(fn, steps, warmup, sampler) / steps
+        prof, ops.PROFILE = ops.PROFILE, None
+        torch.cuda.synchronize(dev)
+        kms = {}
         for name, evs in prof.items():
-            res[name] = sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))
-        return res
+            per_step = len(evs) // (steps + warmup)
+            evs = evs[warmup * per_step:]
+            kms[name] = sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))
+        return ms, kms
 
-    B = WORKLOADS[args.workload] if args.basins is None else args.basins
-    peak, peak_src = measured_peak_gbs()
+    def roofline_of(wl, B, kms, kernel, traffic_key=None):
+        units = B * (wl['T'] if kernel != 'hbv_fwd_warmup' else wl['warm_up'])
+        per_unit = per_unit_bytes(wl, args.ckpt)[kernel]
+        achieved = per_unit * units / (kms[kernel] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if traffic_key and os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(traffic_key, {}).get(kernel)
+            except Exception:
+                traffic = None
+        return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
 
-    # ---------------- device-resident throughput (value) + per-kernel roofline ----------------
-    model, x_host, p_host = build(B, pin=True)
+    # ---------------- the bench workload: device-resident throughput + per-kernel roofline -----
+    wl = WORKLOADS[args.workload]
+    B = wl['B'] if args.basins is None else args.basins
+    T_MAIN = wl['T']
+    model, x_host, p_host = build(wl, B, pin=True)
     x_dev = x_host.to(dev)
     p_dev = p_host.to(dev).requires_grad_(True)
     n0 = _cabi.launch_count()
@@ -289,110 +345,75 @@ def run_b200(args):
     launches_per_step = _cabi.launch_count() - n0
 
     sampler = ClockSampler(local)
-    ops.PROFILE = {}
-    ms_total = timed(lambda: train_step(model, x_dev, p_dev), args.steps, args.warmup, sampler)
-    prof = ops.PROFILE
-    ops.PROFILE = None
-    torch.cuda.synchronize(dev)
-    # keep only the events of the timed steps (drop warm-up)
-    per_step_calls = {k: len(v) // (args.steps + args.warmup) for k, v in prof.items()}
-    prof = {k: v[args.warmup * per_step_calls[k]:] for k, v in prof.items()}
-    kms = kernel_ms(prof)
-    ms_step = ms_total / args.steps
+    ms_step, kms = timed_with_kernels(lambda: train_step(model, x_dev, p_dev), args.steps, args.warmup,
+                                      sampler)
     value = world * B * T_MAIN / (ms_step * 1e-3)
-
     dom = max(kms, key=kms.get)
-    units = B * (T_MAIN if dom != 'hbv_fwd_warmup' else WARM_UP)
-    per_unit = {'hbv_bwd': bytes_bwd(K=args.ckpt), 'hbv_fwd': bytes_fwd(), 'hbv_fwd_warmup': 12.0,
-                'route_fwd': 32.0, 'route_bwd': 24.0}[dom]
-    achieved = per_unit * units / (kms[dom] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[dom],
-                'note': 'c2 has 531 basins x 16 = 8,496 lanes (<3% of one B200 wave): the step is '
-                        'latency-bound, see at_scale.roofline for the throughput regime'}
+    roofline = roofline_of(wl, B, kms, dom, traffic_key=args.workload)
+    if B * NMUL < 148 * 2048 // 4:
+        roofline['note'] = (f'{B} basins x 16 = {B * NMUL} lanes (<{100 * B * NMUL / (148 * 2048):.0f}% of '
+                            'one B200 wave): the step is latency-bound, see at_scale for the '
+                            'throughput regime')
 
-    # ---------------- forward only (inference, no_grad) ----------------
-    def fwd_only():
-        with torch.no_grad():
-            model({'x_phy': x_dev}, p_dev)
-    ms_fwd = timed(fwd_only, args.steps, args.warmup) / args.steps
+    ms_fwd = timed(lambda: fwd_only(model, x_dev, p_dev), args.steps, args.warmup) / args.steps
     fwd = {'value': world * B * T_MAIN / (ms_fwd * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fwd}
 
     # ---------------- end to end with host buffers ----------------
     e2e = None
-    if x_host.is_cuda:   # shard-sized inputs are generated on the device: no host copy to time
-        del x_dev, p_dev, x_host, p_host, model
-        torch.cuda.empty_cache()
-    else:
-        e2e = _e2e(args, dev, world, B, model, x_host, p_host, x_dev, p_dev, train_step, timed)
-        del x_dev, p_dev, x_host, p_host, model
-        torch.cuda.empty_cache()
+    if not x_host.is_cuda:   # shard-sized inputs are generated on the device: no host copy to time
+        e2e = _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_step, timed)
+    del x_dev, p_dev, x_host, p_host, model
+    torch.cuda.empty_cache()
 
-    # ---------------- north-star per-GPU shard ----------------
+    # ---------------- north-star per-GPU shards ----------------
     at_scale = None
     if not args.no_at_scale and args.workload == 'c2' and args.basins is None:
-        Bs = WORKLOADS['shard']
-        model_s, xs, ps = build(Bs, pin=False)
-        ps.requires_grad_(True)
-        ops.PROFILE = {}
-        s_steps, s_warm = 5, 3
-        ms_s = timed(lambda: train_step(model_s, xs, ps), s_steps, s_warm) / s_steps
-        prof_s = ops.PROFILE
-        ops.PROFILE = None
-        pc = {k: len(v) // (s_steps + s_warm) for k, v in prof_s.items()}
-        kms_s = kernel_ms({k: v[s_warm * pc[k]:] for k, v in prof_s.items()})
-        ms_sf = timed(lambda: _nograd(model_s, xs, ps), s_steps, s_warm) / s_steps
-        a_b = bytes_bwd(K=args.ckpt) * Bs * T_MAIN / (kms_s['hbv_bwd'] * 1e-3) / 1e9
-        a_f = bytes_fwd() * Bs * T_MAIN / (kms_s['hbv_fwd'] * 1e-3) / 1e9
-        at_scale = {
-            'workload': f'hbv fwd+bwd, {Bs} basins/GPU x ({WARM_UP} warm-up + {T_MAIN}) days, nmul 16, D2',
-            'value': world * Bs * T_MAIN / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
-            'fwd_value': world * Bs * T_MAIN / (ms_sf * 1e-3), 'fwd_ms_per_step': ms_sf,
-            'kernel_ms': kms_s,
-            'roofline': {'bound': 'hbm', 'kernel': 'hbv_bwd', 'achieved': a_b, 'peak': peak,
-                         'unit': 'GB/s', 'frac': a_b / peak,
-                         'algorithmic_bytes_per_basin_step': bytes_bwd(K=args.ckpt)},
-            'roofline_fwd': {'bound': 'hbm', 'kernel': 'hbv_fwd', 'achieved': a_f, 'peak': peak,
-                             'unit': 'GB/s', 'frac': a_f / peak,
-                             'algorithmic_bytes_per_basin_step': bytes_fwd()},
-        }
-        del model_s, xs, ps
-        torch.cuda.empty_cache()
+        at_scale = {}
+        for name in ('shard', 'c3'):
+            w2 = WORKLOADS[name]
+            Bs = w2['B']
+            model_s, xs, ps = build(w2, Bs, pin=False)
+            ps.requires_grad_(True)
+            s_steps, s_warm = 5, 3
+            ms_s, kms_s = timed_with_kernels(lambda: train_step(model_s, xs, ps), s_steps, s_warm)
+            ms_sf = timed(lambda: fwd_only(model_s, xs, ps), s_steps, s_warm) / s_steps
+            at_scale[name] = {
+                'workload': describe(w2, Bs),
+                'value': world * Bs * w2['T'] / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
+                'fwd_value': world * Bs * w2['T'] / (ms_sf * 1e-3), 'fwd_ms_per_step': ms_sf,
+                'kernel_ms': kms_s,
+                'roofline': roofline_of(w2, Bs, kms_s, 'hbv_bwd', traffic_key=name),
+                'roofline_fwd': roofline_of(w2, Bs, kms_s, 'hbv_fwd', traffic_key=name),
+            }
+            del model_s, xs, ps
+            torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        xc, pc_ = make_inputs(min(B, 531), SEED)
+        Bc = min(B, 531)
+        xc, pc_ = make_inputs(wl, Bc, SEED)
         frac = 1.0 if B <= 531 else 0.5
-        dt, u = cpu_step(xc, pc_, frac)
+        dt, u, wm = cpu_step(wl, xc, pc_, frac)
         cpu_baseline = {'value': u / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                        'sample': f'{min(B, 531)} basins x ({int(WARM_UP * frac)} warm-up + '
-                                  f'{int(T_MAIN * frac)}) days, fwd+bwd, one step, {dt:.1f} s of CPU work'}
+                        'sample': f'{Bc} basins x ({wm[0]} warm-up + {wm[1]}) days, fwd+bwd, one step, '
+                                  f'{dt:.1f} s of CPU work'}
 
     if rank == 0:
+        ncol = wl['n_par'] * NMUL + 2
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {
-                'workload': f'{args.workload}: hbv fwd+bwd training step, {B} basins/GPU x '
-                            f'({WARM_UP} warm-up + {T_MAIN}) days, nmul {NMUL}, dynamic {DYN}, '
-                            f'UH routing + BFI, loss = streamflow.sum()',
-                'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': WARM_UP,
+                'workload': describe(wl, B),
+                'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
                 'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': args.ckpt,
                 'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
                 'l2': 'inputs larger than L2: parameters + gradient = '
-                      f'{2 * (WARM_UP + T_MAIN) * B * (13 * NMUL + 2) * 4 / 1e6:.0f} MB per step vs 126 MB L2',
+                      f'{2 * (wl["warm_up"] + T_MAIN) * B * ncol * 4 / 1e6:.0f} MB per step vs 126 MB L2',
             },
             'clocks': sampler.summary(), 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step,
@@ -406,10 +427,10 @@ def run_b200(args):
     return 0
 
 
-def _e2e(args, dev, world, B, model, x_host, p_host, x_dev, p_dev, train_step, timed):
+def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_step, timed):
     """Same step through the public API with pinned HOST buffers, copies inside the timed region."""
     g_host = torch.empty_like(p_host).pin_memory()
-    q_host = torch.empty(T_MAIN, B, 1).pin_memory()
+    q_host = torch.empty(wl['T'], B, 1).pin_memory()
     l_host = torch.empty(()).pin_memory()
     xd = torch.empty_like(x_dev)
     pd = torch.empty_like(p_dev.detach()).requires_grad_(True)
@@ -428,15 +449,10 @@ def _e2e(args, dev, world, B, model, x_host, p_host, x_dev, p_dev, train_step, t
     ms_e2e = timed(e2e_step, e2e_steps, 3) / e2e_steps
     h2d = x_host.numel() * 4 + p_host.numel() * 4
     d2h = g_host.numel() * 4 + q_host.numel() * 4 + 4
-    return {'value': world * B * T_MAIN / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+    return {'value': world * B * wl['T'] / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-            'what': 'pinned host x_phy + parameters -> device, Hbv.forward + backward, '
+            'what': 'pinned host x_phy + parameters -> device, Model.forward + backward, '
                     'streamflow + loss + parameter gradient -> pinned host'}
-
-
-def _nograd(model, x, p):
-    with torch.no_grad():
-        return model({'x_phy': x}, p)
 
 
 def main():

@@ -5,27 +5,54 @@
 // (hbv_fwd.cu); here each lane walks the segments last-to-first:
 //   pass A  reload the checkpoint, re-run the K-1 forward steps of the segment, pushing the
 //           state *before* every step onto a per-lane stack in shared memory
-//           ([k][state][thread] -> conflict-free, K*20 B per lane);
+//           ([k][thread][state]: 5-word thread stride -> conflict-free, K*20 B per lane);
 //   pass B  pop the states in reverse, re-evaluate the step with its intermediates in
 //           registers and apply the adjoint (hbv_step.cuh: step_bwd).
 // Gradients of time-varying (dynamic) parameters are written per step straight into the
 // caller's packed gradient tensor (column i*nmul + j, through sigmoid' and the affine
 // descale); time-invariant ones accumulate in registers and are written once.
+#include <atomic>
+#include <cstdlib>
 #include "hbv_common.cuh"
 
 namespace hbv {
 
-template <int VAR, bool BETAET, int K, int DM>
+// The order in which the sweep consumes time steps, known in advance: for each segment (last to
+// first) pass A walks t0 .. t0+len-2 forward, pass B walks t0+len-1 .. t0 backward.  The input
+// prefetch (ring or register) simply runs ahead along this sequence.
+struct Sched {
+    int seg, k, len, t0, K, T;
+    bool passB;
+    __device__ __forceinline__ void set_seg() {
+        t0 = seg * K; len = min(T - t0, K); passB = (len <= 1); k = 0;
+    }
+    __device__ __forceinline__ void init(int nseg, int K_, int T_) { K = K_; T = T_; seg = nseg - 1; set_seg(); }
+    // time index of the next request (and whether it belongs to pass B); -1 when exhausted
+    __device__ __forceinline__ int next(bool& isB) {
+        if (seg < 0) { isB = false; return -1; }
+        int t;
+        isB = passB;
+        if (!passB) { t = t0 + k; if (++k == len - 1) { passB = true; k = 0; } }
+        else { t = t0 + len - 1 - k; if (++k == len) { --seg; if (seg >= 0) set_seg(); } }
+        return t;
+    }
+};
+
+template <int VAR, bool BETAET, int DM, bool RING>
 __global__ void __launch_bounds__(128, 4)
 hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
-    extern __shared__ __align__(16) float stack[];   // [K][5][NT]
+    using RS = RingSlots<NPAR, DM>;
+    constexpr int GQ = RS::FIRST_FREE;            // slot of the prefetched dL/dQsim[t, b]
+    constexpr int NSP = (GQ + 1) | 1;             // floats per thread per ring step (odd)
+    extern __shared__ __align__(16) float smem[];  // state stack [K][NT][5] | input ring
 
     const int tid = threadIdx.x;
     const int NT = blockDim.x;
     const int nmul = d.nmul;
+    const int K = d.K;
     const int bl = tid / nmul;
     const int j = tid - bl * nmul;
     const int b_raw = blockIdx.x * d.BPB + bl;
@@ -58,7 +85,15 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     const float* mu_lane = io.muwts ? io.muwts + lane : nullptr;
     const float inv_nmul = 1.0f / (float)nmul;
     float* gdyn_lane = io.gdyn + (int64_t)b * d.dyn_ncol + j;
-    float* my_stack = stack + tid;
+    float* const my_stack = smem + tid * 5;        // + k * NT * 5
+    const int stack_step = NT * 5;
+
+    // The usual training case — upstream gradient on the Qsim series only — gets that one value
+    // per step prefetched with the inputs; any other set of series is loaded where it is used.
+    bool only_q = (io.gflux[HBV_F_QSIM] != nullptr) && (mu_lane == nullptr);
+#pragma unroll
+    for (int f = 1; f < HBV_MAX_FLUX; ++f) only_q = only_q && (io.gflux[f] == nullptr);
+    const float* gq_lane = only_q ? io.gflux[HBV_F_QSIM] + b : nullptr;
 
     // ---- fused zero-fill of the dense gradient tensor (the contract returns d/d(parameters)
     // with the full [T, B, ncol] shape): this CTA's BPB rows of time t are one contiguous run of
@@ -84,28 +119,28 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
 
     Tape tp;
     float F[HBV_MAX_FLUX];
-    // distance-1 input prefetch: `nxt` is requested one full step before it is consumed; the
-    // hand-over is a register copy, so the (large) step body exists once — unrolling it for an
-    // A/B register pair overflowed the instruction cache (ncu: no_instruction stalls)
-    StepIn<DS::NS> nxt;
 
-    auto fwd_only = [&](const StepIn<DS::NS>& in, float (&S)[5]) {
-        apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
-        float P = in.P, PET = in.PET;
+    auto fwd_only = [&](const auto& in, float (&S)[5]) {
+        ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
+        float P = in[0], PET = in[2];
         if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
-        step_fwd<VAR, BETAET, false>(S, p, P, in.T, PET, lc, F, tp);
+        step_fwd<VAR, BETAET, false>(S, p, P, in[1], PET, lc, F, tp);
     };
-    auto rev_step = [&](const StepIn<DS::NS>& in, int t, const float* st) {
+    auto rev_step = [&](const auto& in, int t, const float* st) {
         // upstream gradients of the nmul-reduced series (broadcast over the components)
         float gF[HBV_MAX_FLUX];
-        const int64_t o = (int64_t)t * d.B + b;
 #pragma unroll
-        for (int f = 0; f < HBV_MAX_FLUX; ++f) {
-            gF[f] = 0.f;
-            if (f < TR::NFLUX && io.gflux[f] != nullptr) gF[f] = __ldg(io.gflux[f] + o) * inv_nmul;
+        for (int f = 0; f < HBV_MAX_FLUX; ++f) gF[f] = 0.f;
+        if (only_q) {
+            gF[HBV_F_QSIM] = in[GQ] * inv_nmul;
+        } else {
+            const int64_t o = (int64_t)t * d.B + b;
+#pragma unroll
+            for (int f = 0; f < HBV_MAX_FLUX; ++f)
+                if (f < TR::NFLUX && io.gflux[f] != nullptr) gF[f] = __ldg(io.gflux[f] + o) * inv_nmul;
+            if (mu_lane != nullptr && io.gflux[HBV_F_QSIM] != nullptr)
+                gF[HBV_F_QSIM] = __ldg(io.gflux[HBV_F_QSIM] + o) * __ldg(mu_lane + (int64_t)t * d.muwts_t_stride);
         }
-        if (mu_lane != nullptr && io.gflux[HBV_F_QSIM] != nullptr)
-            gF[HBV_F_QSIM] = __ldg(io.gflux[HBV_F_QSIM] + o) * __ldg(mu_lane + (int64_t)t * d.muwts_t_stride);
         if (io.gstate_series != nullptr) {
             const float* gs = io.gstate_series + (int64_t)t * nlane + lane;
 #pragma unroll
@@ -113,11 +148,11 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         }
         float S[5];
 #pragma unroll
-        for (int s = 0; s < 5; ++s) S[s] = st[s * NT];
-        apply_dyn<NPAR, DM>(d, dynmask, in, p, dpd);
-        float P = in.P, PET = in.PET;
+        for (int s = 0; s < 5; ++s) S[s] = st[s];
+        ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, dpd);
+        float P = in[0], PET = in[2];
         if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
-        step_fwd<VAR, BETAET, true>(S, p, P, in.T, PET, lc, F, tp);
+        step_fwd<VAR, BETAET, true>(S, p, P, in[1], PET, lc, F, tp);
 
         float gp[NPAR];
 #pragma unroll
@@ -135,15 +170,64 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         float* gr = gdyn_lane + (int64_t)t * dyn_tstride;
 #pragma unroll
         for (int i = 0; i < NPAR; ++i) {
-            if (DS::is_dyn(i, dynmask)) { if (valid) gr[d.col[i]] = gp[i] * dpd[i]; }
+            if (DS::is_dyn(i, dynmask)) { if (valid) gr[(unsigned)d.col[i]] = gp[i] * dpd[i]; }
             else gacc[i] += gp[i];
         }
     };
-    auto load_in = [&](StepIn<DS::NS>& in, int t) {
-        load_step<NPAR, DM>(d, fptr, f_tstride, dyn_lane, dyn_tstride, dynmask, min(max(t, 0), d.T - 1), in);
-    };
 
+    // ---- input prefetch along the sweep's schedule -------------------------------------------
     const int nseg = (d.T + K - 1) / K;
+    Sched sch;
+    sch.init(nseg, K, d.T);
+    // RING: per-thread shared-memory ring, one step per cp.async group, nstage - 1 steps ahead
+    const int nstage = d.nstage;
+    const int step_floats = NT * NSP;
+    float* const ring0 = smem + K * stack_step + tid * NSP;
+    float* const ring_end = ring0 + nstage * step_floats;
+    float* wp = ring0;
+    const float* rp = ring0;
+    auto ring_issue = [&]() {
+        bool isB;
+        const int t = sch.next(isB);
+        if (t >= 0) {
+            ring_issue_step<NPAR, DM>(d, fptr + (int64_t)t * f_tstride, dyn_lane + (int64_t)t * dyn_tstride,
+                                      dynmask, wp);
+            if (isB && only_q) cp_async4(wp + GQ, gq_lane + (int64_t)t * d.B);
+        }
+        wp += step_floats;
+        if (wp == ring_end) wp = ring0;
+        cp_async_commit();
+    };
+    auto ring_pop = [&]() -> const float* {       // wait for the oldest step (ring_issue() then
+                                                  // refills the slot consumed one step earlier)
+        ring_wait(nstage);
+        const float* cur = rp;
+        rp += step_floats;
+        if (rp == ring_end) rp = ring0;
+        return cur;
+    };
+    // registers: distance-1 prefetch; `nxt` is requested one full step before it is consumed and
+    // handed over by a register copy, so the (large) step body exists once
+    struct RegInG { float v[GQ + 1]; __device__ __forceinline__ float operator[](int k) const { return v[k]; } };
+    RegInG nxt;
+    auto reg_request = [&]() {
+        bool isB;
+        const int t = sch.next(isB);
+        if (t >= 0) {
+            RegIn<NPAR, DM> tmp;
+            reg_load_step<NPAR, DM>(d, fptr + (int64_t)t * f_tstride, dyn_lane + (int64_t)t * dyn_tstride,
+                                    dynmask, tmp);
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) nxt.v[q] = tmp.v[q];
+            if (isB && only_q) nxt.v[GQ] = __ldg(gq_lane + (int64_t)t * d.B);
+        }
+    };
+    if constexpr (RING) {
+        for (int s = 0; s < nstage - 1; ++s) ring_issue();
+    } else {
+        reg_request();
+    }
+
     for (int seg = nseg - 1; seg >= 0; --seg) {
         const int t0 = seg * K;
         const int len = min(d.T - t0, K);
@@ -154,27 +238,40 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
             for (int s = 0; s < 5; ++s) S[s] = __ldg(ck + s * nlane);
         }
         // ---- pass A: recompute the segment, push the state before every step ---------------
-        if (K > 1) load_in(nxt, t0);
+        float* st = my_stack;
         for (int k = 0; k < len; ++k) {
-            float* st = my_stack + k * 5 * NT;
 #pragma unroll
-            for (int s = 0; s < 5; ++s) st[s * NT] = S[s];
+            for (int s = 0; s < 5; ++s) st[s] = S[s];
+            st += stack_step;
             if (k < len - 1) {
-                const StepIn<DS::NS> cur = nxt;
-                load_in(nxt, t0 + k + 1);
-                fwd_only(cur, S);
+                if constexpr (RING) {
+                    const float* cur = ring_pop();
+                    ring_issue();
+                    fwd_only(cur, S);
+                } else {
+                    const RegInG cur = nxt;
+                    reg_request();
+                    fwd_only(cur, S);
+                }
             }
         }
         // ---- pass B: reverse sweep ---------------------------------------------------------
         const int tl = t0 + len - 1;
-        load_in(nxt, tl);
 #pragma unroll 1
         for (int k = 0; k < len; ++k) {
-            const StepIn<DS::NS> cur = nxt;
-            load_in(nxt, tl - k - 1);
-            rev_step(cur, tl - k, my_stack + (len - 1 - k) * 5 * NT);
+            st -= stack_step;
+            if constexpr (RING) {
+                const float* cur = ring_pop();
+                ring_issue();
+                rev_step(cur, tl - k, st);
+            } else {
+                const RegInG cur = nxt;
+                reg_request();
+                rev_step(cur, tl - k, st);
+            }
         }
     }
+    if constexpr (RING) cp_async_wait<0>();
     // d(par)/d(raw) of the time-invariant parameters: recomputed here instead of being kept
     // live in registers through the sweep
     resolve_params<NPAR, DM>(d, io.dyn, io.sta, io.drop, b, j, p, dpd, &lastmask);
@@ -194,16 +291,19 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     }
 }
 
-template <int VAR, bool BETAET, int K, int DM>
-static int launch_bwd_k(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
+template <int VAR, bool BETAET, int DM, bool RING>
+static int launch_bwd_r(const KDesc& d, const BwdPtrs& io, size_t smem, cudaStream_t st) {
     const int NT = d.BPB * d.nmul;
     const int grid = (d.B + d.BPB - 1) / d.BPB;
-    const size_t smem = (size_t)K * 5 * NT * sizeof(float);
-    auto k = hbv_bwd_kernel<VAR, BETAET, K, DM>;
+    auto k = hbv_bwd_kernel<VAR, BETAET, DM, RING>;
     cudaError_t e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+    static std::atomic<int> optin[HBV_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && dev < HBV_MAX_DEVICES && optin[dev].load(std::memory_order_acquire) == 0) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        optin[dev].store(1, std::memory_order_release);
     }
     k<<<grid, NT, smem, st>>>(d, io);
     count_launch();
@@ -212,24 +312,39 @@ static int launch_bwd_k(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     return (int)e;
 }
 
+// input path by regime, as in hbv_fwd.cu (ring for small grids, registers otherwise)
 template <int VAR, bool BETAET, int DM>
-static int launch_bwd_dm(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
-    switch (d.K) {
-        case 1: return launch_bwd_k<VAR, BETAET, 1, DM>(d, io, st);
-        case 8: return launch_bwd_k<VAR, BETAET, 8, DM>(d, io, st);
-        case 16: return launch_bwd_k<VAR, BETAET, 16, DM>(d, io, st);
-        case 32: return launch_bwd_k<VAR, BETAET, 32, DM>(d, io, st);
+static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
+    if (d.K < 1 || d.K > 64) { set_error("ckpt_interval must be in [1, 64]"); return HBV_E_CKPT; }
+    const int NT = d.BPB * d.nmul;
+    const size_t stack = (size_t)d.K * 5 * NT * sizeof(float);
+    if (stack > 100 * 1024) { set_error("ckpt_interval * nmul too large for the shared-memory state stack"); return HBV_E_CKPT; }
+    if constexpr (DM >= 0) {
+        constexpr int NSP = (RingSlots<Traits<VAR>::NPAR, DM>::FIRST_FREE + 1) | 1;
+        const long long grid = (d.B + d.BPB - 1) / d.BPB;
+        const char* force = std::getenv("HBV_B200_RING");
+        const bool ring = force ? (force[0] == '1') : (grid * NT <= 148LL * 4 * 32 * 2);
+        if (ring) {
+            size_t bytes = 0;
+            d.nstage = choose_nstage(NT, NSP, 1, stack, grid, &bytes);
+            if (d.nstage) return launch_bwd_r<VAR, BETAET, DM, true>(d, io, stack + bytes, st);
+        }
     }
-    set_error("ckpt_interval must be one of 1, 8, 16, 32");
-    return HBV_E_CKPT;
+    return launch_bwd_r<VAR, BETAET, DM, false>(d, io, stack, st);
 }
 
 template <int VAR, bool BETAET>
 static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     const int dm = static_dynmask(d, io.drop != nullptr);
     if (dm == 0) return launch_bwd_dm<VAR, BETAET, 0>(d, io, st);
-    if constexpr (BETAET) {
+    if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
         if (dm == DM_D2) return launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
+    }
+    if constexpr (VAR == HBV_VARIANT_HBV11P) {
+        if (dm == DM_ALL14) return launch_bwd_dm<VAR, BETAET, DM_ALL14>(d, io, st);
+    }
+    if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
+        if (dm == DM_D3) return launch_bwd_dm<VAR, BETAET, DM_D3>(d, io, st);
     }
     return launch_bwd_dm<VAR, BETAET, -1>(d, io, st);
 }

@@ -7,6 +7,8 @@
 
 namespace hbv {
 
+constexpr int HBV_MAX_DEVICES = 64;
+
 // Device-side copy of hbv_desc_t with derived quantities (passed by value as a kernel argument).
 struct KDesc {
     int T, B, nmul, n_par;
@@ -16,6 +18,7 @@ struct KDesc {
     int K;               // checkpoint interval
     int muwts_t_stride;
     int BPB;             // basins per CTA
+    int nstage;          // input ring: cp.async groups in flight + 1 (2..4)
     float nearzero, dt, inv_dt;
     int src[HBV_MAX_PAR];
     int col[HBV_MAX_PAR];
@@ -39,14 +42,14 @@ struct BwdPtrs {
 
 // value in [0,1] (or raw) -> physical parameter
 __device__ __forceinline__ float descale(const KDesc& d, int i, float raw) {
-    const float v = d.apply_sigmoid ? sigmoidf_(raw) : raw;
+    const float v = d.apply_sigmoid ? (i == HBV_P_TT ? sigmoidf_(raw) : sigmoid_sfu(raw)) : raw;
     return v * d.span[i] + d.lo[i];
 }
 
 // d(par)/d(raw) given the physical value is not needed: recompute from raw.
 __device__ __forceinline__ float descale_grad(const KDesc& d, int i, float raw) {
     if (d.apply_sigmoid) {
-        const float s = sigmoidf_(raw);
+        const float s = (i == HBV_P_TT) ? sigmoidf_(raw) : sigmoid_sfu(raw);
         return d.span[i] * s * (1.0f - s);
     }
     return d.span[i];
@@ -55,7 +58,7 @@ __device__ __forceinline__ float descale_grad(const KDesc& d, int i, float raw) 
 // value + derivative with one sigmoid evaluation
 __device__ __forceinline__ void descale_both(const KDesc& d, int i, float raw, float& val, float& dval) {
     if (d.apply_sigmoid) {
-        const float s = sigmoidf_(raw);
+        const float s = (i == HBV_P_TT) ? sigmoidf_(raw) : sigmoid_sfu(raw);
         val = s * d.span[i] + d.lo[i];
         dval = d.span[i] * s * (1.0f - s);
     } else {
@@ -68,6 +71,8 @@ __device__ __forceinline__ void descale_both(const KDesc& d, int i, float raw, f
 // DM >= 0: compile-time bit mask (bit i = parameter i is read from row t of `dyn`); requires
 //          no dropout mask.  DM = -1: runtime mask (any set, dropout allowed).
 constexpr int DM_D2 = (1 << HBV_P_BETA) | (1 << HBV_P_BETAET);   // the reference's shipped set
+constexpr int DM_D3 = DM_D2 | (1 << HBV_P_K0);                   // BASELINE.json configs[3] (hourly)
+constexpr int DM_ALL14 = (1 << 14) - 1;                          // hbv_1_1p, every parameter dynamic (configs[2])
 
 __host__ __device__ constexpr int popc_c(unsigned x) {
     int n = 0;
@@ -154,6 +159,111 @@ __device__ __forceinline__ void apply_dyn(const KDesc& d, uint32_t dynmask,
             if (dpd) { float v, dv; descale_both(d, i, in.raw[DS::slot(i)], v, dv); p[i] = v; dpd[i] = dv; }
             else p[i] = descale(d, i, in.raw[DS::slot(i)]);
         }
+}
+
+// ---- shared-memory input ring (cp.async) ----------------------------------------------------
+// Each thread stages its OWN inputs (3 forcings + the raw values of its dynamic parameters) for
+// the coming time steps with 4-byte cp.async copies (LDGSTS: no registers, no scoreboard slot),
+// `depth = RC * nstage` steps deep, and later reads them back with immediate-offset LDS.  Layout
+// [ring step][thread][NSP] with NSP odd: the per-thread stride is conflict-free and no thread
+// ever reads another thread's slots, so the ring needs no barrier — only cp.async.wait_group.
+// Slot 0..2 = P, T, PET; slot 3 + s = dynamic parameter (s = compact index for a compile-time
+// set, the parameter index for the runtime set); the adjoint adds upstream-gradient slots.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until the oldest of `nstage - 1` outstanding groups has landed
+__device__ __forceinline__ void ring_wait(int nstage) {
+    if (nstage >= 4) cp_async_wait<2>();
+    else if (nstage == 3) cp_async_wait<1>();
+    else cp_async_wait<0>();
+}
+
+template <int NPAR, int DM>
+struct RingSlots {
+    using DS = DynSet<NPAR, DM>;
+    static constexpr int NDS = DS::STATIC ? DS::NDYN : NPAR;     // parameter slots
+    __host__ __device__ static constexpr int par(int i) { return 3 + (DS::STATIC ? DS::slot(i) : i); }
+    static constexpr int FIRST_FREE = 3 + NDS;
+};
+
+// stage the inputs of one time step into `dst` (this thread's NSP floats).  frow / drow point at
+// this thread's forcing row and dynamic-parameter row of that step; column offsets are 32-bit so
+// each address is one IMAD.WIDE
+template <int NPAR, int DM>
+__device__ __forceinline__ void ring_issue_step(const KDesc& d, const float* frow, const float* drow,
+                                                uint32_t dynmask, float* dst) {
+    using DS = DynSet<NPAR, DM>;
+    using RS = RingSlots<NPAR, DM>;
+    cp_async4(dst + 0, frow + (unsigned)d.i_prcp);
+    cp_async4(dst + 1, frow + (unsigned)d.i_tmean);
+    cp_async4(dst + 2, frow + (unsigned)d.i_pet);
+    if (DS::STATIC ? (DM != 0) : (dynmask != 0)) {
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, dynmask)) cp_async4(dst + RS::par(i), drow + (unsigned)d.col[i]);
+    }
+}
+
+// The same inputs held in registers (throughput regime: many resident warps hide the latency,
+// and plain LDG costs the LSU/MIO pipe a third of what LDGSTS + LDS do).  Same slot numbering.
+template <int NPAR, int DM>
+struct RegIn {
+    float v[RingSlots<NPAR, DM>::FIRST_FREE];
+    __device__ __forceinline__ float operator[](int k) const { return v[k]; }
+};
+
+template <int NPAR, int DM>
+__device__ __forceinline__ void reg_load_step(const KDesc& d, const float* frow, const float* drow,
+                                              uint32_t dynmask, RegIn<NPAR, DM>& in) {
+    using DS = DynSet<NPAR, DM>;
+    using RS = RingSlots<NPAR, DM>;
+    in.v[0] = __ldg(frow + (unsigned)d.i_prcp);
+    in.v[1] = __ldg(frow + (unsigned)d.i_tmean);
+    in.v[2] = __ldg(frow + (unsigned)d.i_pet);
+    if (DS::STATIC ? (DM != 0) : (dynmask != 0)) {
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, dynmask)) in.v[RS::par(i)] = __ldg(drow + (unsigned)d.col[i]);
+    }
+}
+
+// descale this step's dynamic parameters from the staged inputs (ring slot or registers)
+template <int NPAR, int DM, typename IN>
+__device__ __forceinline__ void ring_apply_dyn(const KDesc& d, uint32_t dynmask, const IN& in,
+                                               float (&p)[NPAR], float* dpd) {
+    using DS = DynSet<NPAR, DM>;
+    using RS = RingSlots<NPAR, DM>;
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i)
+        if (DS::is_dyn(i, dynmask)) {
+            if (dpd) { float v, dv; descale_both(d, i, in[RS::par(i)], v, dv); p[i] = v; dpd[i] = dv; }
+            else p[i] = descale(d, i, in[RS::par(i)]);
+        }
+}
+
+// Steps per cp.async group: a whole output chunk (4 steps) when a step is a few floats per thread,
+// one step when it is many (runtime set, all-dynamic) so that a deep ring stays small.
+template <int NPAR, int DM>
+struct RingCfg {
+    static constexpr int NSP = RingSlots<NPAR, DM>::FIRST_FREE | 1;   // floats / thread / step (odd)
+    static constexpr int RC = (NSP <= 7) ? 4 : 1;
+};
+
+// host: number of groups (2..4) whose ring fits `budget` bytes next to `fixed` bytes of other
+// shared memory: deep for small grids, where a CTA owns an SM sub-partition and only distance
+// hides latency; shallower when many CTAs share an SM.  0 = does not fit.
+inline int choose_nstage(int NT, int nsp, int rc, size_t fixed, long long grid, size_t* bytes) {
+    const size_t budget = (grid <= 2LL * 148) ? 100 * 1024 : 56 * 1024;
+    const size_t group = (size_t)rc * NT * nsp * sizeof(float);
+    int n = (rc == 1) ? 4 : 3;
+    while (n > 2 && fixed + n * group > budget) --n;
+    *bytes = n * group;
+    return (fixed + n * group <= 100 * 1024) ? n : 0;
 }
 
 // host: the runtime dynamic set as a bit mask, or -1 when a dropout mask forces the generic path

@@ -7,14 +7,17 @@
 //   * parameters are read in place from the caller's packed tensor (column i*nmul + j): a
 //     half-warp reads one 64 B run per parameter, no re-layout pass; sigmoid + affine descale
 //     (hbv.py:201, core/calc/utils.py:24) are fused; static parameters are descaled once;
-//   * forcings and dynamic parameters of step t+PF are loaded while step t computes (register
-//     prefetch ring), so the dependent chain of a step never waits on HBM — this is what the
-//     531-basin configurations (1-2 warps per SM, latency-bound) need;
+//   * forcings and dynamic parameters are staged through a per-thread shared-memory ring with
+//     cp.async (hbv_common.cuh), 2-12 steps ahead of the step that consumes them: the dependent
+//     chain of a step never waits on HBM, the loads hold no registers or scoreboard slots, and
+//     the consuming LDS use immediate offsets (no per-step address arithmetic);
 //   * which parameters are dynamic is a template argument for the common sets (none / the
 //     reference's shipped [parBETA, parBETAET] / all), a runtime mask otherwise;
 //   * the nmul aggregation is a shared-memory transpose-reduce per chunk of TC time steps:
 //     each lane stores its <=12 fluxes as 3x STS.128 into a padded, conflict-free tile, then
 //     (t, basin, flux-quad) work items sum the nmul components and write [T, B] planes.
+#include <atomic>
+#include <cstdlib>
 #include "hbv_common.cuh"
 
 namespace hbv {
@@ -27,15 +30,17 @@ __host__ __device__ inline int tile_bstride(int nmul) {
     return nmul * NFP + 12;
 }
 
-template <int VAR, bool BETAET, bool WRITE_FLUX, int DM>
+template <int VAR, bool BETAET, bool WRITE_FLUX, int DM, bool RING>
 __global__ void __launch_bounds__(256)
 hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
-    using DS = DynSet<NPAR, DM>;
+    constexpr int NSP = RingCfg<NPAR, DM>::NSP;
+    constexpr int RC = RingCfg<NPAR, DM>::RC;
     extern __shared__ __align__(16) float smem[];
 
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;
     const int nmul = d.nmul;
     const int bl = tid / nmul;
     const int j = tid - bl * nmul;
@@ -69,7 +74,6 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
     float* my_slot = smem + bl * bstride + j * NFP;   // + tc * BPB * bstride
     const int tstride_s = d.BPB * bstride;
     const float inv_nmul = 1.0f / (float)nmul;
-    const int NT = blockDim.x;
     const int items = TC * d.BPB * 3;
     // item `tid`: (tc, basin, quad)
     const int r_q = tid % 3;
@@ -94,26 +98,59 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
         if (io.flux[f0 + 3]) io.flux[f0 + 3][o] = acc.w * inv_nmul;
     };
 
-    // ---- double-buffered input prefetch ----------------------------------------------------
-    // Two register buffers of CL steps alternate (A/B): while the steps of one are computed the
-    // loads of the other are in flight.  They are separate named arrays so that ptxas arms their
-    // loads on different scoreboard slots — a wait on a slot waits for every load armed on it.
-    constexpr int CL = DS::CL;
+    // ---- inputs: shared-memory ring (RING, small grids) or register double buffer ------------
+    const float* frow = fptr;       // this thread's rows of the next step to stage / load
+    const float* drow = dyn_lane;
+    int t_issue = 0;
+    // ring (hbv_common.cuh): RC * nstage steps deep
+    const int nstage = d.nstage;
+    const int step_floats = NT * NSP;
+    float* const ring0 = smem + (WRITE_FLUX ? TC * tstride_s : 0) + tid * NSP;
+    float* const ring_end = ring0 + RC * nstage * step_floats;
+    float* wp = ring0;              // next ring group to fill
+    auto issue_group = [&]() {      // RC steps starting at t_issue (nothing beyond T)
+#pragma unroll
+        for (int u = 0; u < RC; ++u) {
+            if (t_issue + u < d.T) {
+                ring_issue_step<NPAR, DM>(d, frow, drow, dynmask, wp + u * step_floats);
+                frow += f_tstride;
+                drow += dyn_tstride;
+            }
+        }
+        t_issue += RC;
+        wp += RC * step_floats;
+        if (wp == ring_end) wp = ring0;
+        cp_async_commit();
+    };
+    const float* rp = ring0;        // next ring group to consume
+    // registers: two named buffers of CL steps alternate (A/B), so that ptxas arms their loads on
+    // different scoreboard slots — a wait on a slot waits for every load armed on it
+    constexpr int CL = DynSet<NPAR, DM>::CL;
     constexpr int NH = TC / CL;
     static_assert(TC % (2 * CL) == 0, "output chunk must hold an even number of prefetch buffers");
-    StepIn<DS::NS> bufA[CL], bufB[CL];
-    auto load_buf = [&](StepIn<DS::NS> (&buf)[CL], int t) {
+    RegIn<NPAR, DM> bufA[CL], bufB[CL];
+    auto load_buf = [&](RegIn<NPAR, DM> (&buf)[CL]) {
 #pragma unroll
-        for (int u = 0; u < CL; ++u)
-            load_step<NPAR, DM>(d, fptr, f_tstride, dyn_lane, dyn_tstride, dynmask, min(t + u, d.T - 1), buf[u]);
+        for (int u = 0; u < CL; ++u) {
+            if (t_issue < d.T) {
+                reg_load_step<NPAR, DM>(d, frow, drow, dynmask, buf[u]);
+                frow += f_tstride;
+                drow += dyn_tstride;
+            }
+            ++t_issue;
+        }
     };
-    load_buf(bufA, 0);
+    if constexpr (RING) {
+        for (int s = 0; s < nstage - 1; ++s) issue_group();
+    } else {
+        load_buf(bufA);
+    }
 
     int ck_next = (d.K > 0 && io.ckpt != nullptr) ? 0 : 0x7fffffff;
     float* ck_ptr = io.ckpt ? io.ckpt + lane : nullptr;
 
     Tape tp;
-    auto do_step = [&](const StepIn<DS::NS>& in, int t, int tc) {
+    auto do_step = [&](const auto& in, int t, int tc) {
         if (t == ck_next) {
             if (valid) {
 #pragma unroll
@@ -122,11 +159,11 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
             ck_ptr += 5 * nlane;
             ck_next += d.K;
         }
-        apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
-        float P = in.P, PET = in.PET;
+        ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
+        float P = in[0], PET = in[2];
         if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
         float F[HBV_MAX_FLUX];
-        step_fwd<VAR, BETAET, false>(S, p, P, in.T, PET, lc, F, tp);
+        step_fwd<VAR, BETAET, false>(S, p, P, in[1], PET, lc, F, tp);
         if (io.state_series != nullptr && valid) {
             float* ss = io.state_series + (int64_t)t * nlane + lane;
 #pragma unroll
@@ -143,18 +180,34 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
 
     for (int t0 = 0; t0 < d.T; t0 += TC) {
         const int tcn = min(TC, d.T - t0);
+        if constexpr (RING) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            if (h % 2 == 0) {
-                load_buf(bufB, t0 + (h + 1) * CL);
+            for (int u = 0; u < TC; ++u) {
+                if (u % RC == 0) {
+                    // the group holding step t0+u has landed; refill the group consumed last
+                    ring_wait(nstage);
+                    issue_group();
+                }
+                if (u < tcn) do_step(rp + (u % RC) * step_floats, t0 + u, u);
+                if ((u + 1) % RC == 0) {
+                    rp += RC * step_floats;
+                    if (rp == ring_end) rp = ring0;
+                }
+            }
+        } else {
 #pragma unroll
-                for (int u = 0; u < CL; ++u)
-                    if (h * CL + u < tcn) do_step(bufA[u], t0 + h * CL + u, h * CL + u);
-            } else {
-                load_buf(bufA, t0 + (h + 1) * CL);
+            for (int h = 0; h < NH; ++h) {
+                if (h % 2 == 0) {
+                    load_buf(bufB);
 #pragma unroll
-                for (int u = 0; u < CL; ++u)
-                    if (h * CL + u < tcn) do_step(bufB[u], t0 + h * CL + u, h * CL + u);
+                    for (int u = 0; u < CL; ++u)
+                        if (h * CL + u < tcn) do_step(bufA[u], t0 + h * CL + u, h * CL + u);
+                } else {
+                    load_buf(bufA);
+#pragma unroll
+                    for (int u = 0; u < CL; ++u)
+                        if (h * CL + u < tcn) do_step(bufB[u], t0 + h * CL + u, h * CL + u);
+                }
             }
         }
         if constexpr (WRITE_FLUX) {
@@ -172,45 +225,79 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
             __syncthreads();
         }
     }
+    if constexpr (RING) cp_async_wait<0>();
     if (valid && io.state_out != nullptr) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) io.state_out[s * nlane + lane] = S[s];
     }
 }
 
-template <int VAR, bool BETAET, int DM>
-static int launch_fwd_dm(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st) {
+template <int VAR, bool BETAET, bool WRITE_FLUX, int DM, bool RING>
+static int launch_fwd_r(const KDesc& d, const FwdPtrs& io, size_t smem, cudaStream_t st) {
     const int NT = d.BPB * d.nmul;
     const int grid = (d.B + d.BPB - 1) / d.BPB;
-    const size_t smem = write_flux ? (size_t)TC * d.BPB * tile_bstride(d.nmul) * sizeof(float) : 0;
+    auto k = hbv_fwd_kernel<VAR, BETAET, WRITE_FLUX, DM, RING>;
     cudaError_t e;
-    if (write_flux) {
-        auto k = hbv_fwd_kernel<VAR, BETAET, true, DM>;
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-        }
-        k<<<grid, NT, smem, st>>>(d, io);
-    } else {
-        hbv_fwd_kernel<VAR, BETAET, false, DM><<<grid, NT, 0, st>>>(d, io);
+    // opt in to > 48 KB of dynamic shared memory once per kernel (and device)
+    static std::atomic<int> optin[HBV_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && dev < HBV_MAX_DEVICES && optin[dev].load(std::memory_order_acquire) == 0) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        optin[dev].store(1, std::memory_order_release);
     }
+    k<<<grid, NT, smem, st>>>(d, io);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) set_error(cudaGetErrorString(e));
     return (int)e;
 }
 
-// pick the compile-time dynamic-parameter set when the runtime one matches it
+// Input path by regime.  Small grids (a CTA or two per SM, e.g. 531 basins): the recurrence is a
+// single dependent chain per warp, only prefetch DISTANCE hides HBM latency -> shared-memory
+// ring.  Large grids: many resident warps hide it and the LSU/MIO pipe is the scarcer resource
+// -> register double buffer.  The runtime-mask kernels (DM = -1) always use registers.
+template <int VAR, bool BETAET, bool WRITE_FLUX, int DM>
+static int launch_fwd_k(KDesc d, const FwdPtrs& io, cudaStream_t st) {
+    using RCfg = RingCfg<Traits<VAR>::NPAR, DM>;
+    size_t tile = WRITE_FLUX ? (size_t)TC * d.BPB * tile_bstride(d.nmul) * sizeof(float) : 0;
+    if constexpr (DM >= 0) {
+        const long long grid = (d.B + d.BPB - 1) / d.BPB;
+        const char* force = std::getenv("HBV_B200_RING");     // 0 / 1: override (experiments)
+        const bool ring = force ? (force[0] == '1') : (grid * d.BPB * d.nmul <= 148LL * 4 * 32 * 2);
+        if (ring) {
+            size_t bytes = 0;
+            d.nstage = choose_nstage(d.BPB * d.nmul, RCfg::NSP, RCfg::RC, tile, grid, &bytes);
+            if (d.nstage) return launch_fwd_r<VAR, BETAET, WRITE_FLUX, DM, true>(d, io, tile + bytes, st);
+        }
+    }
+    if (tile > 100 * 1024) { set_error("nmul too large for the shared-memory output tile"); return HBV_E_NMUL; }
+    return launch_fwd_r<VAR, BETAET, WRITE_FLUX, DM, false>(d, io, tile, st);
+}
+
+// pick the compile-time dynamic-parameter set when the runtime one matches it: none (warm-up /
+// all-static), the reference's shipped [parBETA, parBETAET], BASELINE.json's all-14 (hbv_1_1p)
+// and [parBETA, parK0, parBETAET] (hbv_2 family); any other set, and dropout, take the runtime
+// mask (DM = -1)
 template <int VAR, bool BETAET>
 static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st) {
-    constexpr int NPAR = Traits<VAR>::NPAR;
     const int dm = static_dynmask(d, io.drop != nullptr);
-    if (dm == 0) return launch_fwd_dm<VAR, BETAET, 0>(d, io, write_flux, st);
-    if constexpr (BETAET) {
-        if (dm == DM_D2) return launch_fwd_dm<VAR, BETAET, DM_D2>(d, io, write_flux, st);
+    if (!write_flux) {
+        if (dm == 0) return launch_fwd_k<VAR, BETAET, false, 0>(d, io, st);
+        return launch_fwd_k<VAR, BETAET, false, -1>(d, io, st);
     }
-    (void)NPAR;
-    return launch_fwd_dm<VAR, BETAET, -1>(d, io, write_flux, st);
+    if (dm == 0) return launch_fwd_k<VAR, BETAET, true, 0>(d, io, st);
+    if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
+        if (dm == DM_D2) return launch_fwd_k<VAR, BETAET, true, DM_D2>(d, io, st);
+    }
+    if constexpr (VAR == HBV_VARIANT_HBV11P) {
+        if (dm == DM_ALL14) return launch_fwd_k<VAR, BETAET, true, DM_ALL14>(d, io, st);
+    }
+    if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
+        if (dm == DM_D3) return launch_fwd_k<VAR, BETAET, true, DM_D3>(d, io, st);
+    }
+    return launch_fwd_k<VAR, BETAET, true, -1>(d, io, st);
 }
 
 int make_kdesc(const hbv_desc_t* desc, KDesc& d);  // hbv_cabi.cu

@@ -452,4 +452,15 @@ __device__ __forceinline__ float sigmoidf_(float x) {
     return r;
 }
 
+// SFU sigmoid, 4 instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP), ~3 ulp: used for every parameter
+// except parTT (see above).  With all 14 parameters of hbv_1_1p time-varying the full-accuracy
+// form costs ~250 of ~470 warp instructions per step; this one ~60.
+__device__ __forceinline__ float sigmoid_sfu(float x) {
+#if HBV_MATH == 0
+    return sigmoidf_(x);
+#else
+    return rcp_approx(1.0f + ex2_approx(-1.442695040888963f * x));
+#endif
+}
+
 }  // namespace hbv

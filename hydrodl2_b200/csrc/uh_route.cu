@@ -150,6 +150,9 @@ uh_conv_bwd_kernel(const RDesc d, const float* __restrict__ uh, const float* __r
 
     for (int s = 0; s < d.nser; ++s) {
         const bool has_g = (g_mask >> s) & 1u;
+        // a series with neither an upstream gradient nor a BFI term has an all-zero adjoint:
+        // its g_in plane is left unwritten (the caller skips it, see hbv_b200.h)
+        if (!has_g && !(g_bfi != nullptr && (s == d.bfi_num || s == d.bfi_den))) continue;
         const float cst = (s == d.bfi_num ? gnum : 0.f) + (s == d.bfi_den ? gden : 0.f);
         const float* gs = g_out ? g_out + s * g_stride + b : nullptr;
         const float* xs = x + s * x_stride + b;

@@ -236,7 +236,9 @@ HBV_API int hbv_b200_route_fwd(const hbv_route_desc_t* desc, const float* route,
  * Adjoint of hbv_b200_route_fwd.
  *   g_out     nser planes [T, B] or per-series NULL via g_out_mask bit s
  *   g_bfi     [B] or NULL
- *   g_in      nser planes [T, B] (written)
+ *   g_in      nser planes [T, B]; plane s is written only if series s is live, i.e. bit s of
+ *             g_out_mask is set or g_bfi != NULL and s is bfi_num / bfi_den (a dead series has
+ *             an all-zero adjoint; its plane is left untouched)
  *   g_route   [B, route_stride]: columns 0,1 written (gradient w.r.t. the raw /
  *             [0,1] routing parameters)
  *   ws        workspace [ (lenF + 2) * nchunk * B ] floats

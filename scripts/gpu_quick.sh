@@ -14,7 +14,8 @@ d=json.load(open('gpurun_out/bench_quick.json'))
 print('c2 ms/step', d['ms_per_step'], 'value', d['value'], 'fwd', d['fwd'])
 print('c2 kernels', d['kernel_ms'])
 print('e2e', d['e2e']['ms_per_step'])
-a=d['at_scale']; print('shard ms', a['ms_per_step'], a['kernel_ms'], 'frac bwd', a['roofline']['frac'], 'frac fwd', a['roofline_fwd']['frac'])
+for n, a in d['at_scale'].items():
+    print(n, 'ms %.3f fwd-only %.3f' % (a['ms_per_step'], a['fwd_ms_per_step']), {k: round(v, 3) for k, v in a['kernel_ms'].items()}, 'frac bwd %.3f fwd %.3f' % (a['roofline']['frac'], a['roofline_fwd']['frac']))
 PY
 if [ "$1" == "ncu" ]; then
 ncu --set full --clock-control none --import-source on -k regex:hbv_.*_kernel -s 6 -c 3 -o gpurun_out/prof_shard2 python bench.py --workload shard --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_shard2.log 2>&1
