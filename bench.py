@@ -32,7 +32,6 @@ import math
 import os
 import statistics
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -58,6 +57,8 @@ WORKLOADS = {
                B=22500, label='c3: hbv_1_1p fwd+bwd, all 14 parameters dynamic, 180k basins / 8 GPUs'),
 }
 SEED = 20261017
+# diagnostic only: time the step without the shared-gradient all-reduce
+NO_ALLREDUCE = os.environ.get('HBV_BENCH_NO_ALLREDUCE') == '1'
 
 
 # ----------------------------------------------------------------------------------------------
@@ -73,8 +74,28 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print('max', nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r, flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+    """Samples SM clock + throttle reasons with NVML while the timed region runs.
+
+    The sampling loop lives in a child process (a sampler thread in this process would contend
+    for the GIL with the host-bound step loop and slow the very thing being timed); the parent
+    only notes the wall-clock window of the timed region and filters the child's samples."""
 
     REASONS = {
         0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap',
@@ -83,52 +104,60 @@ class ClockSampler:
     }
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thr = None
+        import subprocess
+        self.t0 = self.t1 = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis else index
         except Exception:
-            self.nv = None
-
-    def _once(self):
+            phys = index
         try:
-            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-            try:
-                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-            except Exception:
-                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            for bit, name in self.REASONS.items():
-                if r & bit and name != 'gpu_idle':
-                    self.reasons.add(name)
+            self.proc = subprocess.Popen([sys.executable, '-c', _SAMPLER_SRC, str(phys)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            pass
-
-    def _loop(self):
-        while not self._stop.is_set():
-            self._once()
-            time.sleep(0.005)
+            self.proc = None
 
     def start(self):
-        if self.nv is not None:
-            self._thr = threading.Thread(target=self._loop, daemon=True)
-            self._thr.start()
+        self.t0 = time.time()
 
     def stop(self):
-        if self._thr is not None:
-            self._stop.set()
-            self._thr.join()
-            self._once()
+        self.t1 = time.time()
 
     def summary(self):
-        if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml unavailable']}
-        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
+        time.sleep(0.01)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        self.proc = None
+        max_mhz, inside, all_s, reasons = None, [], [], set()
+        for ln in out.splitlines():
+            f = ln.split()
+            try:
+                if f[0] == 'max':
+                    max_mhz = int(f[1])
+                    continue
+                ts, mhz, r = float(f[0]), int(f[1]), int(f[2])
+            except Exception:
+                continue
+            all_s.append((ts, mhz))
+            if self.t0 is not None and self.t0 <= ts <= self.t1:
+                inside.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != 'gpu_idle':
+                        reasons.add(name)
+        if not inside and all_s and self.t0 is not None:
+            # timed region shorter than one sampling period: take the nearest sample
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = [min(all_s, key=lambda s: abs(s[0] - mid))[1]]
+        if not inside:
+            return {'sm_mhz': None, 'sm_max_mhz': max_mhz, 'reasons': ['nvml unavailable']}
+        return {'sm_mhz': statistics.median(inside), 'sm_max_mhz': max_mhz,
+                'reasons': sorted(reasons), 'samples': len(inside)}
 
 
 def make_inputs(wl, B, seed, device=None, pin=False):
@@ -256,6 +285,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         print('bench.py: no CUDA device — the B200 arm has no CPU fallback', file=sys.stderr)
         return 2
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     rank, local, world = D.init_from_env()
     if world != args.gpus and rank == 0:
         print(f'bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
@@ -278,7 +310,8 @@ def run_b200(args):
         # gradient of a bias on the static-parameter row shared by all basins (stands in for
         # the shared NN weights): the one quantity that needs a cross-GPU reduction
         gshared = p_dev.grad[-1].sum(dim=0)
-        D.allreduce_shared_grad(gshared)
+        if not NO_ALLREDUCE:
+            D.allreduce_shared_grad(gshared)
         return out, loss, gshared
 
     def fwd_only(model, x, p):
@@ -344,9 +377,22 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     launches_per_step = _cabi.launch_count() - n0
 
-    sampler = ClockSampler(local)
-    ms_step, kms = timed_with_kernels(lambda: train_step(model, x_dev, p_dev), args.steps, args.warmup,
-                                      sampler)
+    sampler = ClockSampler(local)     # child process; up and sampling well before the timed region
+    # per-kernel device times (eager, CUDA events around every C-ABI call)
+    ms_eager, kms = timed_with_kernels(lambda: train_step(model, x_dev, p_dev), args.steps, args.warmup)
+    # the timed step: eager by default; --graph replays the same step from a CUDA graph
+    graph_note = 'eager'
+    step_fn = lambda: train_step(model, x_dev, p_dev)   # noqa: E731
+    if args.graph and world == 1:
+        try:
+            from hydrodl2_b200.graphs import GraphedStep
+            gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev), warmup=3, device=dev)
+            step_fn = gstep.replay
+            graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+        except Exception as exc:   # pragma: no cover - depends on driver / NCCL
+            graph_note = f'eager (graph capture failed: {type(exc).__name__}: {exc})'
+            torch.cuda.synchronize(dev)
+    ms_step = timed(step_fn, args.steps, args.warmup, sampler) / args.steps
     value = world * B * T_MAIN / (ms_step * 1e-3)
     dom = max(kms, key=kms.get)
     roofline = roofline_of(wl, B, kms, dom, traffic_key=args.workload)
@@ -412,6 +458,7 @@ def run_b200(args):
                 'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
                 'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': args.ckpt,
                 'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
+                'launch': graph_note, 'eager_ms_per_step': ms_eager,
                 'l2': 'inputs larger than L2: parameters + gradient = '
                       f'{2 * (wl["warm_up"] + T_MAIN) * B * ncol * 4 / 1e6:.0f} MB per step vs 126 MB L2',
             },
@@ -466,6 +513,8 @@ def main():
     ap.add_argument('--ckpt', type=int, default=16, choices=[1, 8, 16, 32])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')
+    ap.add_argument('--graph', action='store_true',
+                    help='time a CUDA-graph replay of the step (single GPU; measured no faster than eager)')
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == 'reference':

@@ -12,7 +12,7 @@ import os
 
 HBV_MAX_PAR = 20
 HBV_MAX_FLUX = 12
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 VARIANT_HBV, VARIANT_HBV11P, VARIANT_HBV2, VARIANT_HOURLY, VARIANT_ADJ = 0, 1, 2, 3, 4
 SRC_DYN_T, SRC_DYN_LAST, SRC_STA = 0, 1, 2
@@ -51,7 +51,7 @@ class HbvBwdIO(C.Structure):
         ('forcing', _fp), ('dyn', _fp), ('sta', _fp), ('drop', _fp), ('attrs', _fp),
         ('muwts', _fp), ('ckpt', _fp), ('gflux', _fp * HBV_MAX_FLUX), ('gstate_out', _fp),
         ('gstate_series', _fp), ('gdyn', _fp), ('gsta', _fp), ('gstate_in', _fp),
-        ('gdyn_zero_fill', C.c_int32), ('reserved_', C.c_int32),
+        ('gdyn_zero_fill', C.c_int32), ('reserved_', C.c_int32), ('gforcing', _fp), ('gmuwts', _fp),
     ]
 
 

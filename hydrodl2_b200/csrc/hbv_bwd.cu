@@ -119,6 +119,10 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
 
     Tape tp;
     float F[HBV_MAX_FLUX];
+    float gmu_acc = 0.f;
+    // per-basin sum of the forcing gradient over the nmul components: shuffles when the lanes of
+    // a basin are an aligned power-of-two group inside a warp, atomics otherwise
+    const bool shfl_reduce = (nmul & (nmul - 1)) == 0 && nmul <= 32 && (NT % 32 == 0 || NT <= 32);
 
     auto fwd_only = [&](const auto& in, float (&S)[5]) {
         ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
@@ -157,7 +161,29 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         float gp[NPAR];
 #pragma unroll
         for (int i = 0; i < NPAR; ++i) gp[i] = 0.f;
-        step_bwd<VAR, BETAET>(gS, gF, p, PET, lc, tp, gp);
+        float gX[3];
+        step_bwd<VAR, BETAET>(gS, gF, p, PET, lc, tp, gp, gX);
+
+        if (io.gmuwts != nullptr && io.gflux[HBV_F_QSIM] != nullptr) {
+            // Qsim_out = sum_j muwts_j * Qsim_j (hbv.py:511): d/d muwts_j = dL/dQsim_out * Qsim_j
+            const float gm = __ldg(io.gflux[HBV_F_QSIM] + (int64_t)t * d.B + b) * F[HBV_F_QSIM];
+            if (d.muwts_t_stride != 0) { if (valid) io.gmuwts[(int64_t)t * d.muwts_t_stride + lane] = gm; }
+            else gmu_acc += gm;
+        }
+        if (io.gforcing != nullptr) {
+            if constexpr (TR::HOURLY) { gX[0] *= d.inv_dt; gX[2] *= d.inv_dt; }
+            float* gx = io.gforcing + ((int64_t)t * d.B + b) * d.nvar;
+            if (shfl_reduce) {          // the nmul lanes of a basin are an aligned group of a warp
+                for (int o = nmul >> 1; o > 0; o >>= 1) {
+                    gX[0] += __shfl_xor_sync(0xffffffffu, gX[0], o);
+                    gX[1] += __shfl_xor_sync(0xffffffffu, gX[1], o);
+                    gX[2] += __shfl_xor_sync(0xffffffffu, gX[2], o);
+                }
+                if (valid && j == 0) { gx[d.i_prcp] = gX[0]; gx[d.i_tmean] = gX[1]; gx[d.i_pet] = gX[2]; }
+            } else if (valid) {
+                atomicAdd(gx + d.i_prcp, gX[0]); atomicAdd(gx + d.i_tmean, gX[1]); atomicAdd(gx + d.i_pet, gX[2]);
+            }
+        }
 
         if (zmask != 0 && t < d.T - 1) {
             float* z = zrow + (int64_t)t * dyn_tstride;
@@ -288,6 +314,7 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
 #pragma unroll
             for (int s = 0; s < 5; ++s) io.gstate_in[s * nlane + lane] = gS[s];
         }
+        if (io.gmuwts != nullptr && d.muwts_t_stride == 0) io.gmuwts[lane] = gmu_acc;
     }
 }
 
@@ -363,6 +390,7 @@ int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st
     p.attrs = io->attrs; p.muwts = io->muwts; p.ckpt = io->ckpt;
     p.gstate_out = io->gstate_out; p.gstate_series = io->gstate_series;
     p.gdyn = io->gdyn; p.gsta = io->gsta; p.gstate_in = io->gstate_in;
+    p.gforcing = io->gforcing; p.gmuwts = io->muwts ? io->gmuwts : nullptr;
     p.zero_fill = io->gdyn_zero_fill && io->gdyn != nullptr && ((d.BPB * d.dyn_ncol + d.BPB * d.nmul - 1) / (d.BPB * d.nmul) <= 32);
     if (io->gdyn_zero_fill && !p.zero_fill) { set_error("gdyn_zero_fill unsupported for this shape (ncol/nmul > 32)"); return HBV_E_SHAPE; }
     for (int f = 0; f < HBV_MAX_FLUX; ++f) p.gflux[f] = io->gflux[f];

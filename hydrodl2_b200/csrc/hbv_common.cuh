@@ -36,7 +36,7 @@ struct BwdPtrs {
     const float* forcing; const float* dyn; const float* sta; const uint8_t* drop;
     const float* attrs; const float* muwts; const float* ckpt;
     const float* gflux[HBV_MAX_FLUX]; const float* gstate_out; const float* gstate_series;
-    float* gdyn; float* gsta; float* gstate_in;
+    float* gdyn; float* gsta; float* gstate_in; float* gforcing; float* gmuwts;
     int zero_fill;
 };
 

@@ -254,12 +254,13 @@ __device__ __forceinline__ float min_w(float a, float b) {
 }
 
 // Adjoint step.  On entry gS = dL/d(state after the step); gF = dL/d(per-lane fluxes of the
-// step).  On exit gS = dL/d(state before the step) and gp[i] += dL/d(parameter i at this step).
+// step).  On exit gS = dL/d(state before the step), gp[i] += dL/d(parameter i at this step) and
+// gX = dL/d(P, T, PET) of this step as the step uses them (hourly: P, PET already / dt).
 template <int VAR, bool BETAET>
 __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_MAX_FLUX],
                                          const float (&p)[Traits<VAR>::NPAR], float PET,
                                          const LaneConst& c, const Tape& tp,
-                                         float (&gp)[Traits<VAR>::NPAR]) {
+                                         float (&gp)[Traits<VAR>::NPAR], float (&gX)[3]) {
     using TR = Traits<VAR>;
     const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
     auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };       // "* dt"
@@ -349,6 +350,7 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     gSM2 += get2 * wE;
     const float get0 = D(get2 * (1.f - wE));
     const float gef = gF[HBV_F_EVAPFACTOR] + get0 * PET;
+    gX[2] = get0 * tp.ef;                                  // d/dPET (as the step uses it)
     const float gef1 = (tp.ef1 >= 0.f && tp.ef1 <= 1.f) ? gef : 0.f;
     float gef0 = gef1;
     if constexpr (BETAET) {
@@ -425,6 +427,10 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     gTTe -= gmelt0 * p[HBV_P_CFMAX];
     if constexpr (TR::LAT) { if (c.Elev < 2000.f) gp[HBV_P_TT] += gTTe; }
     else gp[HBV_P_TT] += gTTe;
+    // forcings: T enters as T - TTe only (the rain/snow masks carry no gradient);
+    // P = RAIN (T >= TTe, into W) or SNOW (T < TTe, into SP1 = SP + SNOW*dt)
+    gX[1] = -gTTe;
+    gX[0] = (tp.dT >= 0.f) ? gW : D(gSP1);
 
     gS[0] = gSP1; gS[1] = gMW_in; gS[2] = gSM_in; gS[3] = gSUZ_in; gS[4] = gSLZ_in;
     if constexpr (TR::HOURLY) {  // guard rails: clamp(x, min=m) passes where x >= m

@@ -1,0 +1,49 @@
+"""CUDA-graph capture of a whole training / inference step.
+
+The 531-basin configurations are launch- and host-bound: one `Hbv.forward` + `backward` is ~20
+kernel launches and ~1 ms of Python for ~1.1 ms of GPU work.  Every launch of this package goes
+to `torch.cuda.current_stream()` through the C-ABI, allocates nothing itself and never
+synchronises, so the whole step (warm-up run, recurrence, routing, adjoint, the side-stream
+gradient memset, and an NCCL all-reduce if there is one) can be captured once and replayed.
+
+    step = GraphedStep(lambda: train_step(model, x_static, p_static))
+    out, loss = step.outputs          # static tensors, refreshed by every replay
+    step.replay()
+
+Measured on B200 (531 basins): replay is not faster than the eager step (1.45 vs 1.19 ms — the
+side-stream memset branch serialises differently inside a graph), and capturing a step that
+contains an NCCL collective hung on 2 GPUs, so `bench.py` times the eager step; this helper is
+kept for single-GPU inference loops where Python overhead dominates.
+
+Inputs must live in static tensors (copy new data into them before `replay()`); the dynamic-
+parameter dropout draw (`dy_drop > 0`, a CPU RNG draw per forward, hbv.py:240-246) would be
+frozen into the graph, so capture only with `dy_drop == 0` or for inference.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Callable
+
+import torch
+
+
+class GraphedStep:
+    def __init__(self, fn: Callable[[], Any], warmup: int = 3, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('hydrodl2_b200.graphs: CUDA is required (no CPU path)')
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):      # warm-up off the default stream, as capture requires
+            for _ in range(max(1, warmup)):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

@@ -110,6 +110,15 @@ class PackedHbv(torch.nn.Module):
             for _ in self.state_names
         )
 
+    def _init_stack(self, ngrid: int) -> torch.Tensor:
+        """The same initial state as one read-only [5, B, nmul] tensor, built once per shape
+        (the kernels never write their state input)."""
+        c = getattr(self, '_init_cache', None)
+        if c is None or c.shape[1] != ngrid or c.shape[2] != self.nmul or c.device != torch.device(self.device):
+            c = torch.full((5, ngrid, self.nmul), 0.001, dtype=torch.float32, device=self.device)
+            self._init_cache = c
+        return c
+
     def get_states(self) -> Optional[tuple[torch.Tensor, ...]]:
         """Final states of the last forward (SNOWPACK, MELTWATER, SM, SUZ, SLZ)."""
         return self._states_cache
@@ -188,7 +197,7 @@ class PackedHbv(torch.nn.Module):
             warm_up = 0
 
         if (not self.states) or (not self.cache_states):
-            current = torch.stack(self._init_states(ngrid))
+            current = self._init_stack(ngrid)
         else:
             current = torch.stack(tuple(self.states))
 

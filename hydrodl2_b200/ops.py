@@ -146,8 +146,6 @@ def _prep_muwts(muwts, T, B, nmul, dev):
     """-> (contiguous tensor or None, time stride in elements)."""
     if muwts is None:
         return None, 0
-    if muwts.requires_grad:
-        raise NotImplementedError('hydrodl2_b200: gradients w.r.t. `muwts` are not implemented')
     m = muwts.detach().to(device=dev, dtype=torch.float32)
     if m.dim() == 3 and m.shape[0] == T and T > 1:
         return m.expand(T, B, nmul).contiguous(), B * nmul
@@ -189,7 +187,7 @@ class _HbvRun(torch.autograd.Function):
         sta_ncol = 0 if sta is None else sta.shape[-1]
         mu, mu_ts = _prep_muwts(muwts, T, B, nmul, dev)
         d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
-        need_grad = any(t is not None and t.requires_grad for t in (dyn, sta, state_in))
+        need_grad = any(t is not None and t.requires_grad for t in (dyn, sta, state_in, forcing, muwts))
         K = spec.ckpt_interval
         nseg = (T + K - 1) // K
         ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
@@ -248,15 +246,16 @@ class _HbvRun(torch.autograd.Function):
 
         ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
         ctx.has = (dyn is not None, sta is not None)
+        ctx.muwts_shape = None if muwts is None else tuple(muwts.shape)
         ctx.gbuf, ctx.gev = gbuf, gev
         ctx.save_for_backward(forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in)
         ctx.set_materialize_grads(False)
         outs = [flux[f] for f in range(spec.nflux)]
         n_r = spec.n_routed if spec.routing else 0
         outs += [routed[s] for s in range(n_r)]
-        outs.append(bfi if bfi is not None else flux.new_zeros(()))
+        outs.append(bfi)        # None when routing / BFI is off
         outs.append(state_out)
-        outs.append(series if series is not None else flux.new_zeros(()))
+        outs.append(series)     # None unless spec.state_series
         ctx.n_r = n_r
         return tuple(outs)
 
@@ -300,11 +299,19 @@ class _HbvRun(torch.autograd.Function):
         with torch.cuda.device(dev):
             if spec.routing and (any(g is not None for g in g_rout) or g_bfi is not None):
                 mask = 0
-                g_out = torch.empty((n_r, T, B), device=dev, dtype=torch.float32)
-                for s, g in enumerate(g_rout):
-                    if g is not None:
-                        g_out[s].copy_(g)
-                        mask |= 1 << s
+                live = [s for s, g in enumerate(g_rout) if g is not None]
+                for s in live:
+                    mask |= 1 << s
+                if len(live) == 1:
+                    # one routed series has a gradient (the usual streamflow loss): hand its
+                    # plane to the kernel in place — series s is read at base + s * stride
+                    g_keep = g_rout[live[0]].contiguous()
+                    g_out_ptr = g_keep.data_ptr() - live[0] * T * B * 4
+                else:
+                    g_keep = torch.empty((n_r, T, B), device=dev, dtype=torch.float32)
+                    for s in live:
+                        g_keep[s].copy_(g_rout[s])
+                    g_out_ptr = g_keep.data_ptr()
                 g_in = torch.empty((n_r, T, B), device=dev, dtype=torch.float32)
                 if spec.route_src == 'dyn_last':
                     route_t = dyn[dyn.shape[0] - 1, :, spec.route_col:]
@@ -321,7 +328,7 @@ class _HbvRun(torch.autograd.Function):
                 with _timed('route_bwd', dev):
                     A.check(lib.hbv_b200_route_bwd(
                         C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(), T * B, None, T * B,
-                        uh.data_ptr(), _ptr(bfi_ws), g_out.data_ptr(), T * B, mask, _ptr(gb),
+                        uh.data_ptr(), _ptr(bfi_ws), g_out_ptr, T * B, mask, _ptr(gb),
                         g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
                 for s in range(n_r):
                     # a series without upstream gradient (and no BFI term) has an all-zero
@@ -345,9 +352,19 @@ class _HbvRun(torch.autograd.Function):
             io.gdyn_zero_fill = zero_fill
             gstate_in = torch.empty_like(state_in) if state_in.requires_grad else None
             io.gstate_in = _ptr(gstate_in)
+            # f3: gradient w.r.t. the forcings (a by-product of the adjoint sweep) and w.r.t. muwts
+            gforcing = torch.zeros_like(forcing) if ctx.needs_input_grad[1] else None
+            gmu = torch.empty_like(mu) if (mu is not None and ctx.needs_input_grad[7]) else None
+            io.gforcing, io.gmuwts = _ptr(gforcing), _ptr(gmu)
             with _timed('hbv_bwd', dev):
                 A.check(lib.hbv_b200_bwd(C.byref(d), C.byref(io), stream), 'bwd')
-        return (None, None, gdyn_full, gsta, gstate_in, None, None, None, None)
+        if gmu is not None:
+            if g_flux[A.F_QSIM] is None:
+                gmu.zero_()
+            gmu = gmu.view((-1, B, nmul) if mu_ts else (1, B, nmul)).sum_to_size(ctx.muwts_shape)
+        if not (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+            gdyn_full = gsta = None
+        return (None, gforcing, gdyn_full, gsta, gstate_in, None, None, gmu, None)
 
 
 def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, muwts=None,

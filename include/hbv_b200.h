@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HBV_B200_ABI_VERSION 2
+#define HBV_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HBV_API __attribute__((visibility("default")))
@@ -155,6 +155,12 @@ typedef struct hbv_bwd_io {
     float* gstate_in;/* [5, B, nmul] or NULL                                */
     int32_t gdyn_zero_fill;
     int32_t reserved_;
+    float* gforcing; /* [T, B, nvar] or NULL: gradient w.r.t. the forcings (P, T, PET columns),
+                        summed over the nmul components; ZERO-INITIALISED by the caller.  The
+                        rain/snow masks carry no gradient (hbv.py:431-434), T receives it through
+                        melt and refreeze only */
+    float* gmuwts;   /* [T or 1, B, nmul] (same time stride as muwts) or NULL: gradient w.r.t.
+                        the component weights, dL/dQsim[t,b] * Qsim_lane[t,b,j]                 */
 } hbv_bwd_io_t;
 
 /* K1: fused forward recurrence + nmul aggregation (hbv.py:363-511). */
