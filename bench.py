@@ -302,6 +302,9 @@ def run_b200(args):
         model = Model(dict(model_config(wl), ckpt_interval=args.ckpt), device=dev)
         return model, x, p
 
+    def k_eff(wl, B):      # the checkpoint interval the run actually uses (0 = library default)
+        return args.ckpt or int(_cabi.load().hbv_b200_auto_ckpt(wl['T'], B, NMUL))
+
     def train_step(model, x_dev, p_dev):
         p_dev.grad = None
         out = model({'x_phy': x_dev}, p_dev)
@@ -352,7 +355,7 @@ def run_b200(args):
 
     def roofline_of(wl, B, kms, kernel, traffic_key=None):
         units = B * (wl['T'] if kernel != 'hbv_fwd_warmup' else wl['warm_up'])
-        per_unit = per_unit_bytes(wl, args.ckpt)[kernel]
+        per_unit = per_unit_bytes(wl, k_eff(wl, B))[kernel]
         achieved = per_unit * units / (kms[kernel] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -456,7 +459,7 @@ def run_b200(args):
             'config': {
                 'workload': describe(wl, B),
                 'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
-                'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': args.ckpt,
+                'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': k_eff(wl, B),
                 'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
                 'launch': graph_note, 'eager_ms_per_step': ms_eager,
                 'l2': 'inputs larger than L2: parameters + gradient = '
@@ -510,7 +513,8 @@ def main():
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--workload', choices=list(WORKLOADS), default='c2')
     ap.add_argument('--basins', type=int, default=None, help='override basins per GPU')
-    ap.add_argument('--ckpt', type=int, default=16, choices=[1, 8, 16, 32])
+    ap.add_argument('--ckpt', type=int, default=0, choices=[0, 1, 8, 16, 32],
+                    help='checkpoint interval of the adjoint (0 = library default: 1 for small problems, else 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')
     ap.add_argument('--graph', action='store_true',

@@ -93,7 +93,7 @@ EXPORTS = (
     'hbv_b200_fwd', 'hbv_b200_bwd', 'hbv_b200_route_chunks', 'hbv_b200_route_fwd',
     'hbv_b200_route_bwd', 'hbv_b200_abi_version', 'hbv_b200_last_error',
     'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
-    'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd',
+    'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd', 'hbv_b200_auto_ckpt',
 )
 
 _LIB = None
@@ -131,6 +131,8 @@ def load():
     lib.hbv_b200_adj_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjFwdIO), C.c_void_p]
     lib.hbv_b200_adj_bwd.restype = C.c_int
     lib.hbv_b200_adj_bwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjBwdIO), C.c_void_p]
+    lib.hbv_b200_auto_ckpt.restype = C.c_int
+    lib.hbv_b200_auto_ckpt.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.hbv_b200_route_chunks.restype = C.c_int
     lib.hbv_b200_route_chunks.argtypes = [C.c_int32, C.c_int32]
     lib.hbv_b200_route_fwd.restype = C.c_int

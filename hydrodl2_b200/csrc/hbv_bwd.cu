@@ -46,7 +46,8 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     using DS = DynSet<NPAR, DM>;
     using RS = RingSlots<NPAR, DM>;
     constexpr int GQ = RS::FIRST_FREE;            // slot of the prefetched dL/dQsim[t, b]
-    constexpr int NSP = (GQ + 1) | 1;             // floats per thread per ring step (odd)
+    constexpr int CK = GQ + 1;                    // K == 1: the 5 stored states of step t
+    constexpr int NSP = (CK + 5) | 1;             // floats per thread per ring step (odd)
     extern __shared__ __align__(16) float smem[];  // state stack [K][NT][5] | input ring
 
     const int tid = threadIdx.x;
@@ -219,6 +220,11 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
             ring_issue_step<NPAR, DM>(d, fptr + (int64_t)t * f_tstride, dyn_lane + (int64_t)t * dyn_tstride,
                                       dynmask, wp);
             if (isB && only_q) cp_async4(wp + GQ, gq_lane + (int64_t)t * d.B);
+            if (K == 1) {       // every state was stored: stage the state before step t as well
+                const float* ck = io.ckpt + (int64_t)t * 5 * nlane + lane;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) cp_async4(wp + CK + s, ck + s * nlane);
+            }
         }
         wp += step_floats;
         if (wp == ring_end) wp = ring0;
@@ -254,6 +260,15 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         reg_request();
     }
 
+    if (RING && K == 1) {
+        // every state stored (small problems): no recompute pass, the states arrive through
+        // the ring with the inputs
+        for (int t = d.T - 1; t >= 0; --t) {
+            const float* cur = ring_pop();
+            ring_issue();
+            rev_step(cur, t, cur + CK);
+        }
+    } else
     for (int seg = nseg - 1; seg >= 0; --seg) {
         const int t0 = seg * K;
         const int len = min(d.T - t0, K);
@@ -347,7 +362,7 @@ static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     const size_t stack = (size_t)d.K * 5 * NT * sizeof(float);
     if (stack > 100 * 1024) { set_error("ckpt_interval * nmul too large for the shared-memory state stack"); return HBV_E_CKPT; }
     if constexpr (DM >= 0) {
-        constexpr int NSP = (RingSlots<Traits<VAR>::NPAR, DM>::FIRST_FREE + 1) | 1;
+        constexpr int NSP = (RingSlots<Traits<VAR>::NPAR, DM>::FIRST_FREE + 6) | 1;
         const long long grid = (d.B + d.BPB - 1) / d.BPB;
         const char* force = std::getenv("HBV_B200_RING");
         const bool ring = force ? (force[0] == '1') : (grid * NT <= 148LL * 4 * 32 * 2);

@@ -80,6 +80,14 @@ int hbv_b200_abi_version(void) { return HBV_B200_ABI_VERSION; }
 const char* hbv_b200_last_error(void) { return hbv::g_err; }
 int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
 
+int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
+    // small problems (the shared-memory-ring regime of hbv_fwd.cu / hbv_bwd.cu) are latency
+    // bound: store every state (<= 1 GiB) and skip the adjoint's recompute pass; otherwise 16
+    const long long lanes = (long long)B * nmul;
+    if (lanes <= 148LL * 4 * 32 * 2 && lanes * T * 20 <= (1LL << 30)) return 1;
+    return 16;
+}
+
 int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {
     if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
     if (desc->variant == HBV_VARIANT_ADJ) { hbv::set_error("HBV_VARIANT_ADJ runs through hbv_b200_adj_fwd"); return HBV_E_VARIANT; }

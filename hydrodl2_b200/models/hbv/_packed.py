@@ -64,7 +64,9 @@ class PackedHbv(torch.nn.Module):
         self.nmul = 1
         self.cache_states = False
         self.device = device
-        self.ckpt_interval = 16   # K of the checkpointed adjoint (extension, not in reference)
+        # K of the checkpointed adjoint (extension, not in reference): 0 = let the library pick
+        # (every state for small problems, every 16th otherwise), or 1..64
+        self.ckpt_interval = 0
 
         self.states, self._states_cache = None, None
 

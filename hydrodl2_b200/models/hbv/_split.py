@@ -63,7 +63,7 @@ class SplitHbv(torch.nn.Module):
         self.nmul = 1
         self.cache_states = False
         self.device = device
-        self.ckpt_interval = 16
+        self.ckpt_interval = 0    # checkpoint interval of the adjoint: 0 = auto (see _packed.py)
         # extension: hbv_2.py:571-575 materialises 5 x [T, B, nmul] state series on every
         # forward (112 GB at BASELINE config 4).  True = reference behaviour; False keeps only
         # the final states, exposed as series of length 1 so `s[-1]` users keep working.

@@ -76,7 +76,7 @@ class RunSpec:
     nearzero: float = 1e-5
     dt: float = 1.0
     var_index: Sequence[int] = (0, 1, 2)   # prcp, tmean, pet columns
-    ckpt_interval: int = 16
+    ckpt_interval: int = 0     # 0 = auto (hbv_b200_auto_ckpt)
     # routing (core/calc/uh_routing.py); route_src: 'dyn_last' (packed) or 'sta' (split)
     routing: bool = False
     route_src: str = 'dyn_last'
@@ -188,7 +188,8 @@ class _HbvRun(torch.autograd.Function):
         mu, mu_ts = _prep_muwts(muwts, T, B, nmul, dev)
         d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
         need_grad = any(t is not None and t.requires_grad for t in (dyn, sta, state_in, forcing, muwts))
-        K = spec.ckpt_interval
+        K = spec.ckpt_interval or int(lib.hbv_b200_auto_ckpt(T, B, nmul))   # 0 = auto
+        d.ckpt_interval = K
         nseg = (T + K - 1) // K
         ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
         if not need_grad:
@@ -245,6 +246,7 @@ class _HbvRun(torch.autograd.Function):
                                                    _ptr(bfi), _ptr(bfi_ws), stream), 'route_fwd')
 
         ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
+        ctx.K = K
         ctx.has = (dyn is not None, sta is not None)
         ctx.muwts_shape = None if muwts is None else tuple(muwts.shape)
         ctx.gbuf, ctx.gev = gbuf, gev
@@ -340,6 +342,7 @@ class _HbvRun(torch.autograd.Function):
                     g_flux[f] = g_in[s] if g_flux[f] is None else g_flux[f] + g_in[s]
 
             d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
+            d.ckpt_interval = ctx.K
             io = A.HbvBwdIO()
             io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn[t_off:] if dyn is not None else None), _ptr(sta)
             io.drop, io.attrs, io.muwts, io.ckpt = _ptr(drop), _ptr(attrs), _ptr(mu), _ptr(ckpt)
