@@ -131,8 +131,9 @@ def load():
     lib.hbv_b200_adj_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjFwdIO), C.c_void_p]
     lib.hbv_b200_adj_bwd.restype = C.c_int
     lib.hbv_b200_adj_bwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvAdjBwdIO), C.c_void_p]
-    lib.hbv_b200_auto_ckpt.restype = C.c_int
-    lib.hbv_b200_auto_ckpt.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    if hasattr(lib, 'hbv_b200_auto_ckpt'):    # absent only from A/B builds of older sources
+        lib.hbv_b200_auto_ckpt.restype = C.c_int
+        lib.hbv_b200_auto_ckpt.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.hbv_b200_route_chunks.restype = C.c_int
     lib.hbv_b200_route_chunks.argtypes = [C.c_int32, C.c_int32]
     lib.hbv_b200_route_fwd.restype = C.c_int

@@ -39,7 +39,7 @@ struct Sched {
 };
 
 template <int VAR, bool BETAET, int DM, bool RING>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, RING ? 1 : 4)   // RING: small grids, registers are free
 hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
@@ -118,56 +118,61 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     }
     float* zrow = io.gdyn + (int64_t)blockIdx.x * d.BPB * d.dyn_ncol + tid;
 
-    Tape tp;
     float F[HBV_MAX_FLUX];
     float gmu_acc = 0.f;
     // per-basin sum of the forcing gradient over the nmul components: shuffles when the lanes of
     // a basin are an aligned power-of-two group inside a warp, atomics otherwise
     const bool shfl_reduce = (nmul & (nmul - 1)) == 0 && nmul <= 32 && (NT % 32 == 0 || NT <= 32);
 
-    auto fwd_only = [&](const auto& in, float (&S)[5]) {
-        ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);
-        float P = in[0], PET = in[2];
-        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
-        step_fwd<VAR, BETAET, false>(S, p, P, in[1], PET, lc, F, tp);
-    };
-    auto rev_step = [&](const auto& in, int t, const float* st) {
-        // upstream gradients of the nmul-reduced series (broadcast over the components)
+    // One reverse step = (1) `tape_step`: re-evaluate the forward step from its stored state and
+    // keep its intermediates, (2) `adj_step`: apply the adjoint.  (1) of step t-1 does not depend
+    // on (2) of step t, which the every-state-stored sweep below exploits.
+    struct StepCtx {
+        float p[NPAR], dpd[NPAR];
+        Tape tp;
+        float PET, Fq;
         float gF[HBV_MAX_FLUX];
+    };
+    auto tape_step = [&](const auto& in, int t, const float* st, StepCtx& c) {
+        // upstream gradients of the nmul-reduced series (broadcast over the components)
 #pragma unroll
-        for (int f = 0; f < HBV_MAX_FLUX; ++f) gF[f] = 0.f;
+        for (int f = 0; f < HBV_MAX_FLUX; ++f) c.gF[f] = 0.f;
         if (only_q) {
-            gF[HBV_F_QSIM] = in[GQ] * inv_nmul;
+            c.gF[HBV_F_QSIM] = in[GQ] * inv_nmul;
         } else {
             const int64_t o = (int64_t)t * d.B + b;
 #pragma unroll
             for (int f = 0; f < HBV_MAX_FLUX; ++f)
-                if (f < TR::NFLUX && io.gflux[f] != nullptr) gF[f] = __ldg(io.gflux[f] + o) * inv_nmul;
+                if (f < TR::NFLUX && io.gflux[f] != nullptr) c.gF[f] = __ldg(io.gflux[f] + o) * inv_nmul;
             if (mu_lane != nullptr && io.gflux[HBV_F_QSIM] != nullptr)
-                gF[HBV_F_QSIM] = __ldg(io.gflux[HBV_F_QSIM] + o) * __ldg(mu_lane + (int64_t)t * d.muwts_t_stride);
+                c.gF[HBV_F_QSIM] = __ldg(io.gflux[HBV_F_QSIM] + o) * __ldg(mu_lane + (int64_t)t * d.muwts_t_stride);
         }
+        float S[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) S[s] = st[s];
+        ring_apply_dyn<NPAR, DM>(d, dynmask, in, c.p, c.dpd);
+        float P = in[0], PET = in[2];
+        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
+        float Fl[HBV_MAX_FLUX];
+        step_fwd<VAR, BETAET, true>(S, c.p, P, in[1], PET, lc, Fl, c.tp);
+        c.PET = PET;
+        c.Fq = Fl[HBV_F_QSIM];
+    };
+    auto adj_step = [&](const StepCtx& c, int t) {
         if (io.gstate_series != nullptr) {
             const float* gs = io.gstate_series + (int64_t)t * nlane + lane;
 #pragma unroll
             for (int s = 0; s < 5; ++s) gS[s] += __ldg(gs + (int64_t)s * d.T * nlane);
         }
-        float S[5];
-#pragma unroll
-        for (int s = 0; s < 5; ++s) S[s] = st[s];
-        ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, dpd);
-        float P = in[0], PET = in[2];
-        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
-        step_fwd<VAR, BETAET, true>(S, p, P, in[1], PET, lc, F, tp);
-
         float gp[NPAR];
 #pragma unroll
         for (int i = 0; i < NPAR; ++i) gp[i] = 0.f;
         float gX[3];
-        step_bwd<VAR, BETAET>(gS, gF, p, PET, lc, tp, gp, gX);
+        step_bwd<VAR, BETAET>(gS, c.gF, c.p, c.PET, lc, c.tp, gp, gX);
 
         if (io.gmuwts != nullptr && io.gflux[HBV_F_QSIM] != nullptr) {
             // Qsim_out = sum_j muwts_j * Qsim_j (hbv.py:511): d/d muwts_j = dL/dQsim_out * Qsim_j
-            const float gm = __ldg(io.gflux[HBV_F_QSIM] + (int64_t)t * d.B + b) * F[HBV_F_QSIM];
+            const float gm = __ldg(io.gflux[HBV_F_QSIM] + (int64_t)t * d.B + b) * c.Fq;
             if (d.muwts_t_stride != 0) { if (valid) io.gmuwts[(int64_t)t * d.muwts_t_stride + lane] = gm; }
             else gmu_acc += gm;
         }
@@ -197,9 +202,22 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         float* gr = gdyn_lane + (int64_t)t * dyn_tstride;
 #pragma unroll
         for (int i = 0; i < NPAR; ++i) {
-            if (DS::is_dyn(i, dynmask)) { if (valid) gr[(unsigned)d.col[i]] = gp[i] * dpd[i]; }
+            if (DS::is_dyn(i, dynmask)) { if (valid) gr[(unsigned)d.col[i]] = gp[i] * c.dpd[i]; }
             else gacc[i] += gp[i];
         }
+    };
+    StepCtx cA;
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) { cA.p[i] = p[i]; cA.dpd[i] = 0.f; }
+    auto rev_step = [&](const auto& in, int t, const float* st) {
+        tape_step(in, t, st, cA);
+        adj_step(cA, t);
+    };
+    auto fwd_only = [&](const auto& in, float (&S)[5]) {     // pass A: the same parameter copy
+        ring_apply_dyn<NPAR, DM>(d, dynmask, in, cA.p, nullptr);
+        float P = in[0], PET = in[2];
+        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
+        step_fwd<VAR, BETAET, false>(S, cA.p, P, in[1], PET, lc, F, cA.tp);
     };
 
     // ---- input prefetch along the sweep's schedule -------------------------------------------
@@ -261,12 +279,35 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     }
 
     if (RING && K == 1) {
-        // every state stored (small problems): no recompute pass, the states arrive through
-        // the ring with the inputs
-        for (int t = d.T - 1; t >= 0; --t) {
-            const float* cur = ring_pop();
-            ring_issue();
-            rev_step(cur, t, cur + CK);
+        // Every state stored (small problems): no recompute pass, the states arrive through the
+        // ring with the inputs.  One warp owns a scheduler here, so the sweep is software
+        // pipelined: the forward re-evaluation of step t-1 is issued alongside the adjoint of
+        // step t (two independent dependency chains), with two register contexts swapping roles.
+        if constexpr (RING) {
+            StepCtx cB;
+#pragma unroll
+            for (int i = 0; i < NPAR; ++i) { cB.p[i] = p[i]; cB.dpd[i] = 0.f; }
+            int t = d.T - 1;
+            {
+                const float* cur = ring_pop();
+                ring_issue();
+                tape_step(cur, t, cur + CK, cA);
+            }
+            for (; t >= 1; t -= 2) {
+                {
+                    const float* nx = ring_pop();
+                    ring_issue();
+                    tape_step(nx, t - 1, nx + CK, cB);
+                    adj_step(cA, t);
+                }
+                if (t >= 2) {
+                    const float* nx = ring_pop();
+                    ring_issue();
+                    tape_step(nx, t - 2, nx + CK, cA);
+                }
+                adj_step(cB, t - 1);
+            }
+            if (t == 0) adj_step(cA, 0);
         }
     } else
     for (int seg = nseg - 1; seg >= 0; --seg) {
