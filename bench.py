@@ -86,7 +86,7 @@ while True:
     except Exception:
         r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
     print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r, flush=True)
-    time.sleep(0.002)
+    time.sleep(0.025)
 """
 
 
@@ -121,19 +121,24 @@ class ClockSampler:
         self.t0 = time.time()
 
     def stop(self):
+        # the child is ended right here: NVML queries serialise with kernel launches in the
+        # driver, so a sampler left running would slow every later measurement of this process
         self.t1 = time.time()
+        self.out = ''
+        if self.proc is not None:
+            time.sleep(0.03)
+            self.proc.terminate()
+            try:
+                self.out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
+            self.ran = True
 
     def summary(self):
-        if self.proc is None:
+        if not getattr(self, 'ran', False):
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
-        time.sleep(0.01)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ''
-        self.proc = None
+        out = self.out
         max_mhz, inside, all_s, reasons = None, [], [], set()
         for ln in out.splitlines():
             f = ln.split()

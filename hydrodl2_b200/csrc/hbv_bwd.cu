@@ -258,7 +258,8 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     };
     // registers: distance-1 prefetch; `nxt` is requested one full step before it is consumed and
     // handed over by a register copy, so the (large) step body exists once
-    struct RegInG { float v[GQ + 1]; __device__ __forceinline__ float operator[](int k) const { return v[k]; } };
+    // (K == 1: the stored state before step t travels with the inputs of step t, slots CK..CK+4)
+    struct RegInG { float v[CK + 5]; __device__ __forceinline__ float operator[](int k) const { return v[k]; } };
     RegInG nxt;
     auto reg_request = [&]() {
         bool isB;
@@ -270,6 +271,11 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
 #pragma unroll
             for (int q = 0; q < GQ; ++q) nxt.v[q] = tmp.v[q];
             if (isB && only_q) nxt.v[GQ] = __ldg(gq_lane + (int64_t)t * d.B);
+            if (K == 1) {
+                const float* ck = io.ckpt + (int64_t)t * 5 * nlane + lane;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) nxt.v[CK + s] = __ldg(ck + s * nlane);
+            }
         }
     };
     if constexpr (RING) {
@@ -308,6 +314,17 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
                 adj_step(cB, t - 1);
             }
             if (t == 0) adj_step(cA, 0);
+        }
+    } else if (K == 1) {
+        // Every state stored, throughput regime: no recompute pass and no state stack; the
+        // stored state of step t - 1 is requested with its inputs one full step ahead.
+        if constexpr (!RING) {
+#pragma unroll 1
+            for (int t = d.T - 1; t >= 0; --t) {
+                const RegInG cur = nxt;
+                reg_request();
+                rev_step(cur, t, &cur.v[CK]);
+            }
         }
     } else
     for (int seg = nseg - 1; seg >= 0; --seg) {

@@ -81,10 +81,13 @@ const char* hbv_b200_last_error(void) { return hbv::g_err; }
 int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
 
 int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
-    // small problems (the shared-memory-ring regime of hbv_fwd.cu / hbv_bwd.cu) are latency
-    // bound: store every state (<= 1 GiB) and skip the adjoint's recompute pass; otherwise 16
+    // Store every state (20 B per lane-step) whenever that fits 16 GiB of the 180 GB HBM: the
+    // adjoint then needs no recompute pass — a third of its instructions and, with many
+    // time-varying parameters, a second read of the parameter tensor that costs more HBM bytes
+    // than the states do (measured on B200: hbv_1_1p all-dynamic 22.5k basins, K 16 -> 1:
+    // fwd 4.2 -> 4.8 ms, bwd 11.2 -> 7.4 ms).  Longer or wider runs fall back to K = 16.
     const long long lanes = (long long)B * nmul;
-    if (lanes <= 148LL * 4 * 32 * 2 && lanes * T * 20 <= (1LL << 30)) return 1;
+    if (lanes * T * 20 <= (16LL << 30)) return 1;
     return 16;
 }
 

@@ -12,6 +12,7 @@ arithmetic happens in ``libhbv_b200.so``.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -28,8 +29,22 @@ PROFILE = None
 # How the dense [T_total, B, ncol] parameter-gradient tensor gets its zeros:
 #   False (default): allocated and memset on a side stream while the forward kernel runs (the
 #                    forward is FP32-issue bound and leaves HBM idle, so the memset is hidden);
-#   True:            K2 writes every element itself (hbv_bwd_io_t.gdyn_zero_fill = 1).
-FUSED_ZERO_FILL = False
+#   True:            K2 writes every element itself (hbv_bwd_io_t.gdyn_zero_fill = 1);
+#   None (auto):     fused when at least half of the columns are time-varying parameters — K2
+#                    overwrites most of the tensor anyway and a memset would double the HBM
+#                    writes of an HBM-bound run (hbv_1_1p all-dynamic: 14.8 GB per step at the
+#                    22.5k-basin shard); side-stream memset otherwise.
+#   Environment override for experiments: HBV_B200_FUSED_ZERO=0/1.
+FUSED_ZERO_FILL = {'0': False, '1': True}.get(os.environ.get('HBV_B200_FUSED_ZERO', ''), None)
+
+
+def _fused_zero_fill(spec, dyn_ncol) -> bool:
+    if dyn_ncol > 32 * spec.nmul:      # K2's per-thread zero map covers 32 elements per thread
+        return False
+    if FUSED_ZERO_FILL is not None:
+        return bool(FUSED_ZERO_FILL)
+    n_dyn = sum(1 for s in spec.par_src[:spec.n_par] if s == A.SRC_DYN_T)
+    return 2 * n_dyn * spec.nmul >= dyn_ncol
 
 _SIDE_STREAMS = {}
 
@@ -197,7 +212,7 @@ class _HbvRun(torch.autograd.Function):
 
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
         gbuf = gev = None
-        if need_grad and dyn is not None and dyn.requires_grad and not FUSED_ZERO_FILL:
+        if need_grad and dyn is not None and dyn.requires_grad and not _fused_zero_fill(spec, dyn_ncol):
             cur = torch.cuda.current_stream(dev)
             side = _side_stream(dev)
             gbuf = torch.empty_like(dyn)
@@ -286,7 +301,7 @@ class _HbvRun(torch.autograd.Function):
             if ctx.gbuf is not None:
                 gdyn_full, ctx.gbuf = ctx.gbuf, None
                 torch.cuda.current_stream(dev).wait_event(ctx.gev)
-            elif FUSED_ZERO_FILL and dyn_ncol <= 32 * nmul:
+            elif _fused_zero_fill(spec, dyn_ncol):
                 zero_fill = 1
                 gdyn_full = torch.empty_like(dyn)
                 if t_off > 0:

@@ -55,6 +55,26 @@ def test_gradient_matches_reference(case, ckpt):
     assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad K={ckpt}')
 
 
+@pytest.mark.parametrize('ring', ['0', '1'])
+@pytest.mark.parametrize('ckpt', [1, 16])
+@pytest.mark.parametrize('case', PACKED)
+def test_gradient_both_input_paths(case, ckpt, ring, monkeypatch):
+    """The golden cases are small, so by default they take the shared-memory-ring kernels; force
+    each input path (HBV_B200_RING: 0 = register prefetch of the throughput regime, incl. its
+    every-state-stored sweep at K = 1; 1 = cp.async ring) and check fluxes + gradient on both."""
+    monkeypatch.setenv('HBV_B200_RING', ring)
+    dev = torch.device('cuda:0')
+    g = load_golden(case)
+    m, out, p = _run_packed(g, dev, ckpt)
+    loss = 0.0
+    for k, c in g['cot'].items():
+        loss = loss + (out[k] * c.to(dev)).sum()
+    loss.backward()
+    for k, ref in g['out'].items():
+        assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k} ring={ring}')
+    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad K={ckpt} ring={ring}')
+
+
 def test_streamflow_only_gradient_vs_oracle():
     """Typical training use: loss on streamflow only (other flux grads are None)."""
     from oracle import hbv_oracle as O
@@ -78,14 +98,15 @@ def test_streamflow_only_gradient_vs_oracle():
     assert_close(pg.grad, pc.grad, RTOL_GRAD, 'grad')
 
 
+@pytest.mark.parametrize('fused', [True, False])
 @pytest.mark.parametrize('case', ['hbv_d2', 'hbv_d2_drop_nowarm', 'hbv_1_1p_d14'])
-def test_fused_zero_fill_gradient(case):
+def test_fused_zero_fill_gradient(case, fused):
     """K2 writing the whole dense gradient tensor itself (gdyn_zero_fill = 1) into
     uninitialised memory gives the same gradient as the memset path."""
     from hydrodl2_b200 import ops
     dev = torch.device('cuda:0')
     g = load_golden(case)
-    ops.FUSED_ZERO_FILL = True
+    prev, ops.FUSED_ZERO_FILL = ops.FUSED_ZERO_FILL, fused   # default None = by dynamic share
     try:
         torch.empty(1 << 22, device=dev).fill_(float('nan'))   # poison the allocator's free blocks
         m, out, p = _run_packed(g, dev)
@@ -94,8 +115,8 @@ def test_fused_zero_fill_gradient(case):
             loss = loss + (out[k] * c.to(dev)).sum()
         loss.backward()
     finally:
-        ops.FUSED_ZERO_FILL = False
-    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad fused zero-fill')
+        ops.FUSED_ZERO_FILL = prev
+    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad fused zero-fill={fused}')
 
 
 SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3']
