@@ -441,10 +441,16 @@ static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
         if (dm == DM_D2) return launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
     }
     if constexpr (VAR == HBV_VARIANT_HBV11P) {
-        if (dm == DM_ALL14) return launch_bwd_dm<VAR, BETAET, DM_ALL14>(d, io, st);
+        if (dm == DM_ALL14) {
+            const int rc = try_bwd_dense<VAR, BETAET, DM_ALL14>(d, io, st);          // hbv_dense.cu
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_ALL14>(d, io, st);
+        }
     }
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
-        if (dm == DM_D3) return launch_bwd_dm<VAR, BETAET, DM_D3>(d, io, st);
+        if (dm == DM_D3) {
+            const int rc = try_bwd_dense<VAR, BETAET, DM_D3>(d, io, st);
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D3>(d, io, st);
+        }
     }
     return launch_bwd_dm<VAR, BETAET, -1>(d, io, st);
 }

@@ -18,7 +18,8 @@ struct KDesc {
     int K;               // checkpoint interval
     int muwts_t_stride;
     int BPB;             // basins per CTA
-    int nstage;          // input ring: cp.async groups in flight + 1 (2..4)
+    int nstage;          // input ring: cp.async groups in flight + 1 (2..4); hbv_dense.cu: ring slots
+    int slack;           // hbv_dense.cu: 16 when a staged run may start off a 16 B boundary, else 0
     float nearzero, dt, inv_dt;
     int src[HBV_MAX_PAR];
     int col[HBV_MAX_PAR];
@@ -280,7 +281,23 @@ inline int static_dynmask(const KDesc& d, bool has_drop) {
 // issued first, consuming the old values would stall for a full HBM round trip every step.
 __device__ __forceinline__ void order_point() { asm volatile("" ::: "memory"); }
 
+// ---- output staging tile of the forward kernels (nmul reduction through shared memory) --------
+constexpr int NFP = 12;      // floats per lane per step in the staging tile (3 x float4)
+__host__ __device__ inline int tile_bstride(int nmul) {
+    // per-basin stride in floats; +12 keeps 128-bit accesses conflict-free for nmul = 16
+    return nmul * NFP + 12;
+}
+
+// ---- TMA-staged kernels for dense-dynamic runs (hbv_dense.cu) ---------------------------------
+// Return HBV_NOT_ELIGIBLE when the call does not fit them; the caller then launches K1 / K2.
+constexpr int HBV_NOT_ELIGIBLE = -1000;
+template <int VAR, bool BETAET, int DM>
+int try_fwd_dense(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st);
+template <int VAR, bool BETAET, int DM>
+int try_bwd_dense(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
+
 void set_error(const char* msg);
 void count_launch(int n = 1);
+void count_dense_launch();
 
 }  // namespace hbv

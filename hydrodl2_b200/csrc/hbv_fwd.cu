@@ -23,12 +23,6 @@
 namespace hbv {
 
 constexpr int TC = 4;        // time steps per output chunk
-constexpr int NFP = 12;      // floats per lane per step in the staging tile (3 x float4)
-
-__host__ __device__ inline int tile_bstride(int nmul) {
-    // per-basin stride in floats; +12 keeps 128-bit accesses conflict-free for nmul = 16
-    return nmul * NFP + 12;
-}
 
 template <int VAR, bool BETAET, bool WRITE_FLUX, int DM, bool RING>
 __global__ void __launch_bounds__(256)
@@ -292,10 +286,16 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
         if (dm == DM_D2) return launch_fwd_k<VAR, BETAET, true, DM_D2>(d, io, st);
     }
     if constexpr (VAR == HBV_VARIANT_HBV11P) {
-        if (dm == DM_ALL14) return launch_fwd_k<VAR, BETAET, true, DM_ALL14>(d, io, st);
+        if (dm == DM_ALL14) {
+            const int rc = try_fwd_dense<VAR, BETAET, DM_ALL14>(d, io, true, st);   // hbv_dense.cu
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_ALL14>(d, io, st);
+        }
     }
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
-        if (dm == DM_D3) return launch_fwd_k<VAR, BETAET, true, DM_D3>(d, io, st);
+        if (dm == DM_D3) {
+            const int rc = try_fwd_dense<VAR, BETAET, DM_D3>(d, io, true, st);
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_D3>(d, io, st);
+        }
     }
     return launch_fwd_k<VAR, BETAET, true, -1>(d, io, st);
 }

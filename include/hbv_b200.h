@@ -300,11 +300,15 @@ HBV_API int hbv_b200_pair_route_bwd(const hbv_pair_desc_t* desc, const float* pa
 HBV_API int hbv_b200_abi_version(void);
 HBV_API const char* hbv_b200_last_error(void);
 /* checkpoint interval the library recommends for hbv_b200_fwd/bwd on a problem of this size:
- * 1 (store every state, no recompute pass in the adjoint) for small, latency-bound problems,
- * 16 otherwise */
+ * 1 (store every state — 20 B per lane-step — and skip the adjoint's recompute pass) while the
+ * stored states fit 16 GiB, 16 otherwise */
 HBV_API int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul);
 /* number of kernels this library has launched in this process (bench accounting) */
 HBV_API int64_t hbv_b200_launch_count(void);
+/* how many of those were the TMA-staged kernels of hbv_dense.cu (K1d / K2d), which
+ * hbv_b200_fwd / hbv_b200_bwd select by themselves for dense-dynamic runs on large grids
+ * (set HBV_B200_DENSE=0 in the environment to keep K1 / K2) */
+HBV_API int64_t hbv_b200_dense_launches(void);
 
 #ifdef __cplusplus
 }
