@@ -276,7 +276,7 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -290,9 +290,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         print('bench.py: no CUDA device — the B200 arm has no CPU fallback', file=sys.stderr)
         return 2
-    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION / WARN level
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+        os.environ.pop('NCCL_DEBUG')
     rank, local, world = D.init_from_env()
     if world != args.gpus and rank == 0:
         print(f'bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
@@ -475,7 +475,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'fwd': fwd, 'kernel_ms': kms,
             'at_scale': at_scale,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -483,7 +483,12 @@ def run_b200(args):
 
 
 def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_step, timed):
-    """Same step through the public API with pinned HOST buffers, copies inside the timed region."""
+    """Same step through the public API with pinned HOST buffers, every copy inside the timed
+    region.  Two loops are timed: `serial` (upload, step, download, wait — one after the other) and
+    the reported one, `hydrodl2_b200.hostio.PipelinedSteps` (double-buffered inputs on three
+    streams, so a step's upload and the previous step's download overlap the kernels; every step
+    still moves its own inputs and results)."""
+    from hydrodl2_b200.hostio import PipelinedSteps
     g_host = torch.empty_like(p_host).pin_memory()
     q_host = torch.empty(wl['T'], B, 1).pin_memory()
     l_host = torch.empty(()).pin_memory()
@@ -501,13 +506,43 @@ def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_ste
         torch.cuda.current_stream(dev).synchronize()   # the caller needs the results on the host
 
     e2e_steps = max(3, min(args.steps, 20))
-    ms_e2e = timed(e2e_step, e2e_steps, 3) / e2e_steps
+    ms_serial = timed(e2e_step, e2e_steps, 3) / e2e_steps
+    del xd, pd, g_host, q_host, l_host
+
+    def pipe_step(inp):
+        out, loss, _ = train_step(model, inp['x_phy'], inp['parameters'])
+        return {'streamflow': out['streamflow'], 'loss': loss, 'grad': inp['parameters'].grad}
+
+    host_in = {'x_phy': x_host, 'parameters': p_host}
+    pipe = PipelinedSteps(pipe_step, host_in, dev, leaf_names=('parameters',))
+
+    def pipe_run(n):
+        for _ in range(n):
+            pipe.step(host_in)
+        pipe.drain()      # every upload, kernel and download of the n steps has completed
+
+    pipe_run(3)
+    torch.cuda.synchronize(dev)
+    from hydrodl2_b200 import dist as D
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipe_run(e2e_steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    D.barrier()
+    ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev) / e2e_steps
     h2d = x_host.numel() * 4 + p_host.numel() * 4
-    d2h = g_host.numel() * 4 + q_host.numel() * 4 + 4
+    d2h = p_host.numel() * 4 + wl['T'] * B * 4 + 4
     return {'value': world * B * wl['T'] / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'serial_ms_per_step': ms_serial,
+            'pcie_GBps': {'h2d': h2d / (ms_e2e * 1e-3) / 1e9, 'd2h': d2h / (ms_e2e * 1e-3) / 1e9},
             'what': 'pinned host x_phy + parameters -> device, Model.forward + backward, '
-                    'streamflow + loss + parameter gradient -> pinned host'}
+                    'streamflow + loss + parameter gradient -> pinned host; double-buffered on '
+                    'upload / compute / download streams (hydrodl2_b200.hostio.PipelinedSteps), '
+                    'each step moves its own inputs and results; serial_ms_per_step = the same '
+                    'loop without overlap'}
 
 
 def main():
@@ -526,9 +561,24 @@ def main():
                     help='time a CUDA-graph replay of the step (single GPU; measured no faster than eager)')
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    # stdout carries exactly one JSON line: while the run is in progress file descriptor 1 points at
+    # stderr (library banners written by native code land there), the line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference(args)
     return run_b200(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 if __name__ == '__main__':

@@ -474,8 +474,8 @@ hbv_bwd_dense_kernel(const KDesc d, const BwdPtrs io) {
             // <= 3 floats on either side of the aligned core
             if (tid < (int)(head >> 2) && (uint32_t)tid * 4 < pn)
                 reinterpret_cast<float*>(gdst)[tid] = reinterpret_cast<const float*>(ob + shg)[tid];
-            if (tid >= 32 && tid - 32 < (int)(tail >> 2)) {
-                const uint32_t off = head + core + (uint32_t)(tid - 32) * 4;
+            if (tid >= 4 && tid - 4 < (int)(tail >> 2)) {
+                const uint32_t off = head + core + (uint32_t)(tid - 4) * 4;
                 *reinterpret_cast<float*>(gdst + off) = *reinterpret_cast<const float*>(ob + shg + off);
             }
         }
@@ -518,18 +518,28 @@ static bool layout_matches(const KDesc& d) {
     return true;
 }
 
-static bool dense_enabled() {
-    const char* e = std::getenv("HBV_B200_DENSE");       // 0: always take K1/K2 (A/B experiments)
-    return !(e && e[0] == '0');
+// HBV_B200_DENSE: 0 = always K1 / K2, 2 = take the dense kernels whenever the shapes allow it
+// (tests), unset / 1 = where they win
+static int dense_mode() {
+    const char* e = std::getenv("HBV_B200_DENSE");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
 }
 
-// common gate: compile-time dynamic set (dm >= 0, no dropout), nmul 16, the dynamic columns are at
-// least half of a row, large grid (the small-grid regime keeps the cp.async ring kernels)
+// Common gate: compile-time dynamic set (dm > 0, no dropout), nmul 16, the dynamic columns are at
+// least half of a row.  By default additionally: at least 8 time-varying parameters (>= 512 B of
+// parameter bytes per basin-step, the HBM-bound regime) on a grid that fills every resident CTA
+// slot of the GPU.  Measured on B200: with 3 dynamic parameters (hbv_2 family, 22.5k basins) K2
+// beats K2d (4.7 vs 5.8 ms) — the per-step barrier and mbarrier round trip outweigh the saved
+// load instructions — and on small grids (BASELINE configs[3], 2,500 units) the recurrence is
+// latency-bound, where K2d's per-step synchronisation costs 45.7 vs 30.9 ms.
 static bool dense_shape_ok(const KDesc& d, int dm) {
-    if (!dense_enabled() || dm <= 0 || d.nmul != DNM) return false;
-    if (2 * popc_c((unsigned)dm) * DNM < d.dyn_ncol) return false;
+    const int mode = dense_mode();
+    if (mode == 0 || dm <= 0 || d.nmul != DNM) return false;
+    const int ndyn = popc_c((unsigned)dm);
+    if (2 * ndyn * DNM < d.dyn_ncol) return false;
     const long long lanes = (long long)d.B * DNM;
-    return lanes > 148LL * 4 * 32 * 2;
+    if (mode == 2) return lanes > 148LL * 4 * 32 * 2;
+    return ndyn >= 8 && lanes >= 148LL * 16 * 32;
 }
 
 // 0 when every staged run of every CTA and time step starts on a 16 B boundary (then no slot
@@ -593,7 +603,8 @@ static int launch_fwd_dense(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT>
 static int launch_bwd_dense(KDesc d, const BwdPtrs& io, cudaStream_t st) {
-    d.BPB = 128 / DNM;
+    d.BPB = env_int("HBV_B200_DENSE_BPB", 128 / DNM);
+    if (d.BPB != 2 && d.BPB != 4 && d.BPB != 8) d.BPB = 128 / DNM;
     d.slack = run_slack(d, io.dyn, io.forcing, io.gdyn, io.gflux[HBV_F_QSIM]);
     const DenseGeom g = dense_geom(d);
     const size_t fixed = 64 + 2 * (size_t)g.obytes;
@@ -601,7 +612,8 @@ static int launch_bwd_dense(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     int ns = env_int("HBV_B200_DENSE_NS_BWD", 0);
     if (ns <= 0) {
         ns = 6;
-        while (ns > 2 && fixed + ns * slot > smem_budget_4cta()) --ns;
+        const size_t budget = ((size_t)(227 * 1024) / (4 * (128 / DNM) / d.BPB)) - 1024;   // 16 warps / SM
+        while (ns > 2 && fixed + ns * slot > budget) --ns;
     }
     if (ns < 2 || ns > 8 || fixed + ns * slot > 200 * 1024) return HBV_NOT_ELIGIBLE;
     d.nstage = ns;

@@ -221,7 +221,6 @@ class _HbvRun(torch.autograd.Function):
                 gbuf.zero_()
                 gev = torch.cuda.Event()
                 gev.record(side)
-            gbuf.record_stream(side)
 
         flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
         state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
@@ -260,6 +259,12 @@ class _HbvRun(torch.autograd.Function):
                                                    T * B, routed.data_ptr(), T * B, uh.data_ptr(),
                                                    _ptr(bfi), _ptr(bfi_ws), stream), 'route_fwd')
 
+        if gev is not None:
+            # Everything enqueued on this stream from here on runs after the memset (K1 and the
+            # routing above overlap it).  That also makes the buffer safe to hand back to this
+            # stream's allocator pool at any later point without `record_stream`, whose deferred
+            # reuse forces a fresh multi-GB cudaMalloc every step on large shards.
+            torch.cuda.current_stream(dev).wait_event(gev)
         ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
         ctx.K = K
         ctx.has = (dyn is not None, sta is not None)

@@ -1,7 +1,8 @@
 """GPU parity of the TMA-staged kernels (hbv_dense.cu: K1d / K2d).
 
 The golden fixtures are small and run through the cp.async-ring kernels, so these cases use
-basin counts large enough for the dense path (> 2,368 basins at nmul 16) and compare it with
+basin counts large enough for the dense path (> 2,368 basins at nmul 16; HBV_B200_DENSE=2 takes
+it wherever the shapes allow, the default additionally asks for a full-GPU grid) and compare it with
   * the CPU oracle (fp32 restatement of the reference, pinned by tests/test_oracle_golden.py) on
     the same seeded inputs: 1e-5 fluxes/states, 1e-4 parameter gradients (max-norm relative);
   * K1/K2 on the same inputs (HBV_B200_DENSE=0): the step arithmetic is the same code, so the
@@ -30,7 +31,7 @@ def _launches():
 
 def _run_11p(x, p, dev, dense, monkeypatch, cot=None, ckpt=0):
     import hydrodl2_b200 as hydrodl2
-    monkeypatch.setenv('HBV_B200_DENSE', '1' if dense else '0')
+    monkeypatch.setenv('HBV_B200_DENSE', '2' if dense else '0')   # 2 = wherever the shapes allow
     M = hydrodl2.load_model('hbv_1_1p', ver_name='Hbv_1_1p')
     m = M({'warm_up': 0, 'dynamic_params': {'Hbv_1_1p': D14}, 'nmul': NMUL, 'ckpt_interval': ckpt}, device=dev)
     pg = p.to(dev).requires_grad_(True)
@@ -105,7 +106,7 @@ def test_dense_is_taken(monkeypatch):
 
 def _run_split(model, cls, x_dict, params, dev, dense, monkeypatch, **cfg):
     import hydrodl2_b200 as hydrodl2
-    monkeypatch.setenv('HBV_B200_DENSE', '1' if dense else '0')
+    monkeypatch.setenv('HBV_B200_DENSE', '2' if dense else '0')   # 2 = wherever the shapes allow
     M = hydrodl2.load_model(model, ver_name=cls)
     m = M({'dynamic_params': {cls: D3}, 'nmul': NMUL, **cfg}, device=dev)
     ps = [q.detach().clone().requires_grad_(True) for q in params]
@@ -150,7 +151,7 @@ def test_dense_hbv_2_hourly_matches_k1_k2(monkeypatch):
 
     def run(dense):
         import hydrodl2_b200 as hydrodl2
-        monkeypatch.setenv('HBV_B200_DENSE', '1' if dense else '0')
+        monkeypatch.setenv('HBV_B200_DENSE', '2' if dense else '0')   # 2 = wherever the shapes allow
         M = hydrodl2.load_model('hbv_2_hourly', ver_name='Hbv_2_hourly')
         m = M({'dynamic_params': {'Hbv_2_hourly': D3}, 'nmul': NMUL, **cfg}, device=dev)
         m.use_distr_routing = False
