@@ -409,8 +409,9 @@ def run_b200(args):
                             'one B200 wave): the step is latency-bound, see at_scale for the '
                             'throughput regime')
 
-    ms_fwd = timed(lambda: fwd_only(model, x_dev, p_dev), args.steps, args.warmup) / args.steps
-    fwd = {'value': world * B * T_MAIN / (ms_fwd * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fwd}
+    ms_fwd, kms_fwd = timed_with_kernels(lambda: fwd_only(model, x_dev, p_dev), args.steps, args.warmup)
+    fwd = {'value': world * B * T_MAIN / (ms_fwd * 1e-3), 'unit': UNIT, 'ms_per_step': ms_fwd,
+           'kernel_ms': kms_fwd}
 
     # ---------------- end to end with host buffers ----------------
     e2e = None
@@ -430,12 +431,12 @@ def run_b200(args):
             ps.requires_grad_(True)
             s_steps, s_warm = 5, 3
             ms_s, kms_s = timed_with_kernels(lambda: train_step(model_s, xs, ps), s_steps, s_warm)
-            ms_sf = timed(lambda: fwd_only(model_s, xs, ps), s_steps, s_warm) / s_steps
+            ms_sf, kms_sf = timed_with_kernels(lambda: fwd_only(model_s, xs, ps), s_steps, s_warm)
             at_scale[name] = {
                 'workload': describe(w2, Bs),
                 'value': world * Bs * w2['T'] / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
                 'fwd_value': world * Bs * w2['T'] / (ms_sf * 1e-3), 'fwd_ms_per_step': ms_sf,
-                'kernel_ms': kms_s,
+                'kernel_ms': kms_s, 'fwd_kernel_ms': kms_sf,
                 'roofline': roofline_of(w2, Bs, kms_s, 'hbv_bwd', traffic_key=name),
                 'roofline_fwd': roofline_of(w2, Bs, kms_s, 'hbv_fwd', traffic_key=name),
             }

@@ -438,7 +438,10 @@ static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     const int dm = static_dynmask(d, io.drop != nullptr);
     if (dm == 0) return launch_bwd_dm<VAR, BETAET, 0>(d, io, st);
     if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
-        if (dm == DM_D2) return launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
+        if (dm == DM_D2) {
+            const int rc = try_bwd_lean<VAR, BETAET, DM_D2>(d, io, st);              // hbv_lean.cu
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
+        }
     }
     if constexpr (VAR == HBV_VARIANT_HBV11P) {
         if (dm == DM_ALL14) {
@@ -448,7 +451,8 @@ static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     }
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
         if (dm == DM_D3) {
-            const int rc = try_bwd_dense<VAR, BETAET, DM_D3>(d, io, st);
+            int rc = try_bwd_dense<VAR, BETAET, DM_D3>(d, io, st);
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_bwd_lean<VAR, BETAET, DM_D3>(d, io, st);
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D3>(d, io, st);
         }
     }

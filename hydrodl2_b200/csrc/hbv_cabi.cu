@@ -9,12 +9,14 @@ namespace hbv {
 static thread_local char g_err[256] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_dense_launches{0};
+static std::atomic<long long> g_lean_launches{0};
 
 void set_error(const char* msg) {
     std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void count_dense_launch() { g_dense_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_lean_launch() { g_lean_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fwd_dispatch(const hbv_desc_t* desc, const hbv_fwd_io_t* io, cudaStream_t st);
 int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st);
@@ -82,6 +84,7 @@ int hbv_b200_abi_version(void) { return HBV_B200_ABI_VERSION; }
 const char* hbv_b200_last_error(void) { return hbv::g_err; }
 int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
 int64_t hbv_b200_dense_launches(void) { return (int64_t)hbv::g_dense_launches.load(); }
+int64_t hbv_b200_lean_launches(void) { return (int64_t)hbv::g_lean_launches.load(); }
 
 int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
     // Store every state (20 B per lane-step) whenever that fits 16 GiB of the 180 GB HBM: the

@@ -296,8 +296,15 @@ int try_fwd_dense(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream
 template <int VAR, bool BETAET, int DM>
 int try_bwd_dense(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
 
+// ---- lean kernels for the standard layout in the throughput regime (hbv_lean.cu) ---------------
+template <int VAR, bool BETAET, int DM>
+int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st);
+template <int VAR, bool BETAET, int DM>
+int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
+
 void set_error(const char* msg);
 void count_launch(int n = 1);
 void count_dense_launch();
+void count_lean_launch();
 
 }  // namespace hbv

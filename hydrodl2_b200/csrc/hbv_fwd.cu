@@ -283,7 +283,10 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
     }
     if (dm == 0) return launch_fwd_k<VAR, BETAET, true, 0>(d, io, st);
     if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
-        if (dm == DM_D2) return launch_fwd_k<VAR, BETAET, true, DM_D2>(d, io, st);
+        if (dm == DM_D2) {
+            const int rc = try_fwd_lean<VAR, BETAET, DM_D2>(d, io, true, st);       // hbv_lean.cu
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_D2>(d, io, st);
+        }
     }
     if constexpr (VAR == HBV_VARIANT_HBV11P) {
         if (dm == DM_ALL14) {
@@ -293,7 +296,8 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
     }
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
         if (dm == DM_D3) {
-            const int rc = try_fwd_dense<VAR, BETAET, DM_D3>(d, io, true, st);
+            int rc = try_fwd_dense<VAR, BETAET, DM_D3>(d, io, true, st);
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_fwd_lean<VAR, BETAET, DM_D3>(d, io, true, st);
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_D3>(d, io, st);
         }
     }

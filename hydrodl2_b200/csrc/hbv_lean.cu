@@ -1,0 +1,398 @@
+// hbv_lean.cu — K1s / K2s: K1 (hbv_fwd.cu) and the every-state sweep of K2 (hbv_bwd.cu) compiled
+// for the layout the reference actually produces, in the throughput regime (large grids).
+//
+// ncu on the north-star shard (22,500 basins, `hbv` with the shipped dynamic set
+// [parBETA, parBETAET]; profiles/r01_ncu_shard_d2.md) showed both kernels bound by instruction
+// issue, and more than half of the issued instructions were not HBV arithmetic: 64-bit address
+// arithmetic re-derived every step from runtime column numbers and strides (5 instructions per
+// 4-byte load, 10 per gradient store, 23 for the five stored-state loads), the generic sweep
+// schedule, per-step tests of options nobody had switched on (muwts, state series, forcing
+// gradients, per-series upstream gradients, zero fill), descale constants re-read from the
+// constant bank.  The kernels here take all of that out of the loop for the common case:
+//   * forcing columns (prcp, tmean, pet) = (0, 1, 2) of a 3-wide x_phy, nmul = 16, parameter i at
+//     column 16*i (packed form, hbv.py:201-208) or dynamic parameter s at 16*s (split form,
+//     hbv_2.py:211-230): every load / store is `[running pointer + immediate]`;
+//   * five running pointers advanced by a constant stride per step (forcing row, parameter row,
+//     gradient row, upstream-gradient row, stored states), the stored states walked as ONE
+//     pointer because consecutive (t, state) planes are equidistant;
+//   * a compile-time dynamic set, compile-time sigmoid, descale constants in registers;
+//   * adjoint: upstream gradient on the streamflow series only (the training loss), so the other
+//     eleven series' adjoint terms fold away at compile time.
+// Anything else (dropout masks, muwts, state series, other cotangents, other layouts, K > 1)
+// takes K1 / K2.  Arithmetic is the same hbv_step.cuh code: results agree with K1 / K2 to fp32
+// contraction noise (tests/test_lean_gpu.py).
+//
+// Reference spans replaced: models/hbv/hbv.py:423-511, hbv_1_1p.py:422-524, hbv_2.py:464-585,
+// hbv_2_hourly.py:527-683 and PyTorch autograd over them.
+#include <atomic>
+#include <cstdlib>
+#include "hbv_common.cuh"
+
+namespace hbv {
+
+constexpr int LNM = 16;      // components per basin
+constexpr int LBPB = 8;      // basins per CTA (128 threads)
+constexpr int LTC = 4;       // forward: time steps per output chunk
+
+template <int NPAR, int DM, int LAYOUT>
+__host__ __device__ constexpr int lean_col(int i) {
+    return (LAYOUT == 0 ? i : DynSet<NPAR, DM>::slot(i)) * LNM;
+}
+
+template <bool SIG>
+__device__ __forceinline__ float lean_descale(int i, float raw, float span, float lo) {
+    if constexpr (SIG) {
+        const float s = (i == HBV_P_TT) ? sigmoidf_(raw) : sigmoid_sfu(raw);
+        return fmaf(s, span, lo);
+    } else {
+        return fmaf(raw, span, lo);
+    }
+}
+
+template <bool SIG>
+__device__ __forceinline__ void lean_descale_both(int i, float raw, float span, float lo, float& v, float& dv) {
+    if constexpr (SIG) {
+        const float s = (i == HBV_P_TT) ? sigmoidf_(raw) : sigmoid_sfu(raw);
+        v = fmaf(s, span, lo);
+        dv = span * s * (1.0f - s);
+    } else {
+        v = fmaf(raw, span, lo);
+        dv = span;
+    }
+}
+
+// ================================================================================================
+// K1s: forward.  CK: store the state before every step (K = 1) for the adjoint.
+// ================================================================================================
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK>
+__global__ void __launch_bounds__(128, 6)
+hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
+    using TR = Traits<VAR>;
+    constexpr int NPAR = TR::NPAR;
+    using DS = DynSet<NPAR, DM>;
+    constexpr int ND = DS::NDYN;
+    extern __shared__ __align__(16) float tile[];
+
+    const int tid = threadIdx.x;
+    const int bl = tid >> 4, j = tid & 15;
+    const int b_raw = blockIdx.x * LBPB + bl;
+    const bool valid = b_raw < d.B;
+    const int b = valid ? b_raw : d.B - 1;
+    const int64_t lane = (int64_t)b * LNM + j;
+    const int64_t nlane = (int64_t)d.B * LNM;
+
+    LaneConst lc;
+    lc.nearzero = d.nearzero; lc.dt = d.dt; lc.inv_dt = d.inv_dt;
+    lc.Ac = 0.f; lc.Elev = 0.f; lc.lfexp = 0.f;
+    if constexpr (TR::LAT) init_lane_const(lc, __ldg(io.attrs + b), __ldg(io.attrs + d.B + b));
+
+    float p[NPAR];
+    resolve_params<NPAR, DM>(d, io.dyn, io.sta, nullptr, b, j, p, nullptr, nullptr);
+    float dspan[ND], dlo[ND];
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i)
+        if (DS::is_dyn(i, 0)) { dspan[DS::slot(i)] = d.span[i]; dlo[DS::slot(i)] = d.lo[i]; }
+
+    float S[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) S[s] = __ldg(io.state_in + s * nlane + lane);
+
+    // running pointers (advanced by a constant stride per step)
+    const float* pf = io.forcing + (int64_t)b * 3;
+    const float* pd = io.dyn + (int64_t)b * d.dyn_ncol + j;
+    const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
+    float* pk = CK ? io.ckpt + lane : nullptr;       // (t, state) planes are nlane apart
+
+    struct In { float P, T, E; float raw[ND]; };
+    int t_issue = 0;
+    auto load = [&](In& in) {
+        in.P = __ldg(pf); in.T = __ldg(pf + 1); in.E = __ldg(pf + 2);
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0)) in.raw[DS::slot(i)] = __ldg(pd + lean_col<NPAR, DM, LAYOUT>(i));
+        if (++t_issue < d.T) { pf += sf; pd += sd; }   // the last row is simply loaded again
+    };
+
+    // output staging tile + this thread's reduce item (hbv_fwd.cu)
+    constexpr int bstride = LNM * NFP + 12;
+    constexpr int tstride_s = LBPB * bstride;
+    float* const my_slot = tile + bl * bstride + j * NFP;
+    constexpr float inv_nmul = 1.0f / (float)LNM;
+    constexpr int items = LTC * LBPB * 3;            // 96 <= 128 threads
+    const int r_q = tid % 3;
+    const int r_r = tid / 3;
+    const int r_bl = r_r % LBPB;
+    const int r_tc = r_r / LBPB;
+    const int r_bb = blockIdx.x * LBPB + r_bl;
+    const bool r_ok = (tid < items) && (r_bb < d.B);
+    const float* const r_src = tile + r_tc * tstride_s + r_bl * bstride + r_q * 4;
+    int64_t r_o = (int64_t)r_tc * d.B + (r_ok ? r_bb : 0);     // this item's element of its four planes
+    const int64_t r_adv = (int64_t)LTC * d.B;
+
+    Tape tp;
+    auto do_step = [&](const In& in, int tc) {
+        if constexpr (CK) {
+#pragma unroll
+            for (int s = 0; s < 5; ++s) { if (valid) *pk = S[s]; pk += nlane; }
+        }
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0)) p[i] = lean_descale<SIG>(i, in.raw[DS::slot(i)], dspan[DS::slot(i)], dlo[DS::slot(i)]);
+        float P = in.P, PET = in.E;
+        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
+        float F[HBV_MAX_FLUX];
+        step_fwd<VAR, BETAET, false>(S, p, P, in.T, PET, lc, F, tp);
+        float4* o4 = reinterpret_cast<float4*>(my_slot + tc * tstride_s);
+        o4[0] = make_float4(F[0], F[1], F[2], F[3]);
+        o4[1] = make_float4(F[4], F[5], F[6], F[7]);
+        o4[2] = make_float4(F[8], F[9], F[10], TR::NFLUX > 11 ? F[11] : 0.f);
+    };
+
+    // two named prefetch buffers of two steps each (see hbv_fwd.cu: loads in flight must not
+    // share a scoreboard slot with the values being consumed)
+    In A0, A1, B0, B1;
+    load(A0); load(A1);
+    for (int t0 = 0; t0 < d.T; t0 += LTC) {
+        const int tcn = min(LTC, d.T - t0);
+        load(B0); load(B1);
+        do_step(A0, 0);
+        if (1 < tcn) do_step(A1, 1);
+        load(A0); load(A1);
+        if (2 < tcn) do_step(B0, 2);
+        if (3 < tcn) do_step(B1, 3);
+        __syncthreads();
+        if (r_ok && r_tc < tcn) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < LNM; ++jj) {
+                const float4 v = *reinterpret_cast<const float4*>(r_src + jj * NFP);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            float* const* pl = io.flux + r_q * 4;
+            pl[0][r_o] = acc.x * inv_nmul;
+            pl[1][r_o] = acc.y * inv_nmul;
+            pl[2][r_o] = acc.z * inv_nmul;
+            if (r_q * 4 + 3 < TR::NFLUX) pl[3][r_o] = acc.w * inv_nmul;
+        }
+        r_o += r_adv;
+        __syncthreads();
+    }
+    if (valid && io.state_out != nullptr) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) io.state_out[s * nlane + lane] = S[s];
+    }
+}
+
+// ================================================================================================
+// K2s: adjoint, every state stored (K = 1), upstream gradient on the streamflow series
+// ================================================================================================
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
+__global__ void __launch_bounds__(128, 4)
+hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
+    using TR = Traits<VAR>;
+    constexpr int NPAR = TR::NPAR;
+    using DS = DynSet<NPAR, DM>;
+    constexpr int ND = DS::NDYN;
+
+    const int tid = threadIdx.x;
+    const int bl = tid >> 4, j = tid & 15;
+    const int b_raw = blockIdx.x * LBPB + bl;
+    const bool valid = b_raw < d.B;
+    const int b = valid ? b_raw : d.B - 1;
+    const int64_t lane = (int64_t)b * LNM + j;
+    const int64_t nlane = (int64_t)d.B * LNM;
+
+    LaneConst lc;
+    lc.nearzero = d.nearzero; lc.dt = d.dt; lc.inv_dt = d.inv_dt;
+    lc.Ac = 0.f; lc.Elev = 0.f; lc.lfexp = 0.f;
+    if constexpr (TR::LAT) init_lane_const(lc, __ldg(io.attrs + b), __ldg(io.attrs + d.B + b));
+
+    float p[NPAR], gacc[NPAR];
+    resolve_params<NPAR, DM>(d, io.dyn, io.sta, nullptr, b, j, p, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) gacc[i] = 0.f;
+    float dspan[ND], dlo[ND];
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i)
+        if (DS::is_dyn(i, 0)) { dspan[DS::slot(i)] = d.span[i]; dlo[DS::slot(i)] = d.lo[i]; }
+
+    float gS[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) gS[s] = io.gstate_out ? __ldg(io.gstate_out + s * nlane + lane) : 0.f;
+
+    // running pointers, positioned on step T-1 and walked backwards
+    const int64_t row_last = (int64_t)(d.T - 1) * d.B + b;
+    const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
+    const float* pf = io.forcing + row_last * 3;
+    const float* pd = io.dyn + row_last * d.dyn_ncol + j;
+    const float* pq = io.gflux[HBV_F_QSIM] + row_last;
+    const float* pc = io.ckpt + (int64_t)d.T * 5 * nlane + lane;     // one plane past (T-1, state 4)
+    float* pg = io.gdyn + row_last * d.dyn_ncol + j;
+    constexpr float inv_nmul = 1.0f / (float)LNM;
+
+    struct In { float P, T, E, q; float raw[ND]; float S[5]; };
+    auto load = [&](In& in) {
+        in.P = __ldg(pf); in.T = __ldg(pf + 1); in.E = __ldg(pf + 2);
+        in.q = __ldg(pq);
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0)) in.raw[DS::slot(i)] = __ldg(pd + lean_col<NPAR, DM, LAYOUT>(i));
+#pragma unroll
+        for (int s = 4; s >= 0; --s) { pc -= nlane; in.S[s] = __ldg(pc); }
+        pf -= sf; pd -= sd; pq -= d.B;
+    };
+
+    Tape tp;
+    In nxt;
+    load(nxt);
+#pragma unroll 1
+    for (int t = d.T - 1; t >= 0; --t) {
+        const In cur = nxt;
+        if (t > 0) load(nxt);
+
+        float dpd[ND];
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0))
+                lean_descale_both<SIG>(i, cur.raw[DS::slot(i)], dspan[DS::slot(i)], dlo[DS::slot(i)], p[i], dpd[DS::slot(i)]);
+        float S[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) S[s] = cur.S[s];
+        float P = cur.P, PET = cur.E;
+        if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
+        float Fl[HBV_MAX_FLUX];
+        step_fwd<VAR, BETAET, true>(S, p, P, cur.T, PET, lc, Fl, tp);
+
+        float gF[HBV_MAX_FLUX];
+#pragma unroll
+        for (int f = 0; f < HBV_MAX_FLUX; ++f) gF[f] = 0.f;
+        gF[HBV_F_QSIM] = cur.q * inv_nmul;
+        float gp[NPAR];
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i) gp[i] = 0.f;
+        float gX[3];
+        step_bwd<VAR, BETAET>(gS, gF, p, PET, lc, tp, gp, gX);
+
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i) {
+            if (DS::is_dyn(i, 0)) { if (valid) pg[lean_col<NPAR, DM, LAYOUT>(i)] = gp[i] * dpd[DS::slot(i)]; }
+            else gacc[i] += gp[i];
+        }
+        pg -= sd;
+    }
+
+    // static parameters: d(par)/d(raw) recomputed here, written once (as in hbv_bwd.cu)
+    float dps[NPAR];
+    uint32_t lastmask = 0;
+    resolve_params<NPAR, DM>(d, io.dyn, io.sta, nullptr, b, j, p, dps, &lastmask);
+    if (valid) {
+        float* glast = io.gdyn + row_last * d.dyn_ncol + j;
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i) {
+            if (i < d.n_par && !DS::is_dyn(i, 0)) {
+                if (lastmask & (1u << i)) glast[d.col[i]] = gacc[i] * dps[i];
+                else if (io.gsta != nullptr) io.gsta[(int64_t)b * d.sta_ncol + d.col[i] + j] = gacc[i] * dps[i];
+            }
+        }
+        if (io.gstate_in != nullptr) {
+#pragma unroll
+            for (int s = 0; s < 5; ++s) io.gstate_in[s * nlane + lane] = gS[s];
+        }
+    }
+}
+
+// ================================================================================================
+// host: eligibility + launch
+// ================================================================================================
+template <int NPAR, int DM, int LAYOUT>
+static bool lean_layout_matches(const KDesc& d) {
+    for (int i = 0; i < NPAR; ++i)
+        if ((DM >> i) & 1)
+            if (d.col[i] != lean_col<NPAR, DM, LAYOUT>(i)) return false;
+    return true;
+}
+
+static bool lean_common_ok(const KDesc& d) {
+    const char* e = std::getenv("HBV_B200_LEAN");        // 0: always K1 / K2 (A/B experiments)
+    if (e && e[0] == '0') return false;
+    if (d.nmul != LNM || d.nvar != 3 || d.i_prcp != 0 || d.i_tmean != 1 || d.i_pet != 2) return false;
+    // throughput regime only: the small-grid regime keeps the cp.async ring kernels
+    const char* force = std::getenv("HBV_B200_RING");
+    if (force) return force[0] == '0';
+    return (long long)d.B * LNM > 148LL * 4 * 32 * 2;
+}
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
+static int launch_fwd_lean(KDesc d, const FwdPtrs& io, cudaStream_t st) {
+    d.BPB = LBPB;
+    const size_t smem = (size_t)LTC * LBPB * (LNM * NFP + 12) * sizeof(float);
+    const int grid = (d.B + LBPB - 1) / LBPB;
+    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    count_launch();
+    count_lean_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+    return (int)e;
+}
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
+static int launch_bwd_lean(KDesc d, const BwdPtrs& io, cudaStream_t st) {
+    d.BPB = LBPB;
+    const int grid = (d.B + LBPB - 1) / LBPB;
+    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG><<<grid, LBPB * LNM, 0, st>>>(d, io);
+    count_launch();
+    count_lean_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+    return (int)e;
+}
+
+template <int VAR, bool BETAET, int DM>
+int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st) {
+    constexpr int NPAR = Traits<VAR>::NPAR;
+    if (!write_flux || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
+    if (io.drop != nullptr || io.muwts != nullptr || io.state_series != nullptr) return HBV_NOT_ELIGIBLE;
+    if (io.ckpt != nullptr && d.K != 1) return HBV_NOT_ELIGIBLE;
+    for (int f = 0; f < Traits<VAR>::NFLUX; ++f)
+        if (io.flux[f] == nullptr) return HBV_NOT_ELIGIBLE;
+    const bool sig = d.apply_sigmoid != 0;
+    if (lean_layout_matches<NPAR, DM, 0>(d))
+        return sig ? launch_fwd_lean<VAR, BETAET, DM, 0, true>(d, io, st) : launch_fwd_lean<VAR, BETAET, DM, 0, false>(d, io, st);
+    if (lean_layout_matches<NPAR, DM, 1>(d))
+        return sig ? launch_fwd_lean<VAR, BETAET, DM, 1, true>(d, io, st) : launch_fwd_lean<VAR, BETAET, DM, 1, false>(d, io, st);
+    return HBV_NOT_ELIGIBLE;
+}
+
+template <int VAR, bool BETAET, int DM>
+int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
+    constexpr int NPAR = Traits<VAR>::NPAR;
+    if (d.K != 1 || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
+    if (io.drop != nullptr || io.muwts != nullptr || io.gmuwts != nullptr || io.gforcing != nullptr ||
+        io.gstate_series != nullptr || io.gdyn == nullptr) return HBV_NOT_ELIGIBLE;
+    // the caller asked for every element to be written (gdyn_zero_fill): fine when every column
+    // of `dyn` is a time-varying parameter (split form), otherwise K2's zero-fill path
+    if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol) return HBV_NOT_ELIGIBLE;
+    if (io.gflux[HBV_F_QSIM] == nullptr) return HBV_NOT_ELIGIBLE;
+    for (int f = 1; f < HBV_MAX_FLUX; ++f)
+        if (io.gflux[f] != nullptr) return HBV_NOT_ELIGIBLE;
+    const bool sig = d.apply_sigmoid != 0;
+    if (lean_layout_matches<NPAR, DM, 0>(d))
+        return sig ? launch_bwd_lean<VAR, BETAET, DM, 0, true>(d, io, st) : launch_bwd_lean<VAR, BETAET, DM, 0, false>(d, io, st);
+    if (lean_layout_matches<NPAR, DM, 1>(d))
+        return sig ? launch_bwd_lean<VAR, BETAET, DM, 1, true>(d, io, st) : launch_bwd_lean<VAR, BETAET, DM, 1, false>(d, io, st);
+    return HBV_NOT_ELIGIBLE;
+}
+
+// the compiled (variant, dynamic set) pairs: the sets hbv_fwd.cu / hbv_bwd.cu specialise, minus
+// all-dynamic hbv_1_1p (HBM-bound: hbv_dense.cu)
+template int try_fwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_fwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_fwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_fwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_bwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
+template int try_bwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
+template int try_bwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
+template int try_bwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
+
+}  // namespace hbv

@@ -309,6 +309,9 @@ HBV_API int64_t hbv_b200_launch_count(void);
  * hbv_b200_fwd / hbv_b200_bwd select by themselves for dense-dynamic runs on large grids
  * (set HBV_B200_DENSE=0 in the environment to keep K1 / K2) */
 HBV_API int64_t hbv_b200_dense_launches(void);
+/* ... and how many were the standard-layout kernels of hbv_lean.cu (K1s / K2s), selected the same
+ * way for the shipped dynamic sets on large grids (HBV_B200_LEAN=0 keeps K1 / K2) */
+HBV_API int64_t hbv_b200_lean_launches(void);
 
 #ifdef __cplusplus
 }

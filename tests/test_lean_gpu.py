@@ -1,0 +1,171 @@
+"""GPU parity of the standard-layout kernels (hbv_lean.cu: K1s / K2s).
+
+They serve the throughput regime (large grids), so the cases use > 2,368 basins and compare
+  * `hbv` / `hbv_1_1p` with the shipped dynamic set against the CPU oracle on the same seeded
+    inputs (1e-5 fluxes / states, 1e-4 gradients), with warm-up, partial last CTA, odd B;
+  * every variant against K1 / K2 on the same inputs (HBV_B200_LEAN=0): same step arithmetic,
+    agreement to fp32 contraction noise (1e-6);
+and check through the library's dispatch counter that the lean kernels are the ones that ran.
+"""
+
+import pytest
+import torch
+
+from conftest import RTOL_FLUX, RTOL_GRAD, assert_close
+
+pytestmark = pytest.mark.gpu
+
+NMUL = 16
+D2 = ['parBETA', 'parBETAET']
+D3 = ['parBETA', 'parK0', 'parBETAET']
+
+
+def _lean_count():
+    from hydrodl2_b200 import _cabi
+    return _cabi.load().hbv_b200_lean_launches()
+
+
+def _run_packed(model, cls, npar, x, p, dev, lean, monkeypatch, warm_up):
+    import hydrodl2_b200 as hydrodl2
+    monkeypatch.setenv('HBV_B200_LEAN', '1' if lean else '0')
+    M = hydrodl2.load_model(model, ver_name=cls)
+    m = M({'warm_up': warm_up, 'dynamic_params': {cls: D2}, 'nmul': NMUL}, device=dev)
+    pg = p.to(dev).requires_grad_(True)
+    out = m({'x_phy': x.to(dev)}, pg)
+    out['streamflow'].sum().backward()
+    torch.cuda.synchronize()
+    return out, pg.grad, m
+
+
+@pytest.mark.parametrize('model,cls,npar', [('hbv', 'Hbv', 13), ('hbv_1_1p', 'Hbv_1_1p', 14)])
+@pytest.mark.parametrize('B', [2500, 2501])
+def test_lean_packed_vs_oracle(model, cls, npar, B, monkeypatch):
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, warm = 41, 6
+    x = O.synthetic_forcing(T, B, seed=41)
+    p = torch.randn(T, B, npar * NMUL + 2, generator=torch.Generator().manual_seed(42))
+    pc = p.clone().requires_grad_(True)
+    ref, ref_states = O.forward_packed(model, x, pc, nmul=NMUL, warm_up=warm, dynamic_params=D2)
+    ref['streamflow'].sum().backward()
+
+    n0 = _lean_count()
+    out, grad, m = _run_packed(model, cls, npar, x, p, dev, True, monkeypatch, warm)
+    assert _lean_count() - n0 == 2, 'K1s + K2s should have run'
+    for k, v in ref.items():
+        assert_close(out[k], v, RTOL_FLUX, f'lean {model} B={B}:{k}')
+    assert_close(grad, pc.grad, RTOL_GRAD, f'lean {model} B={B}:grad')
+    for name, s, r in zip(m.state_names, m.get_states(), ref_states):
+        assert_close(s, r, RTOL_FLUX, f'lean {model} B={B}:state {name}')
+
+    n0 = _lean_count()
+    out0, grad0, _ = _run_packed(model, cls, npar, x, p, dev, False, monkeypatch, warm)
+    assert _lean_count() - n0 == 0
+    for k in ref:
+        assert_close(out[k], out0[k], 1e-6, f'lean vs K1 {model} B={B}:{k}')
+    assert_close(grad, grad0, 1e-6, f'lean vs K2 {model} B={B}:grad')
+
+
+def test_lean_forward_only_no_grad(monkeypatch):
+    """Inference (no checkpoints): K1s without the state stores."""
+    from oracle import hbv_oracle as O
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    T, B = 23, 2440
+    x = O.synthetic_forcing(T, B, seed=43)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(44))
+    ref, _ = O.forward_packed('hbv', x, p, nmul=NMUL, warm_up=0, dynamic_params=D2)
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'warm_up': 0, 'dynamic_params': {'Hbv': D2}, 'nmul': NMUL}, device=dev)
+    n0 = _lean_count()
+    with torch.no_grad():
+        out = m({'x_phy': x.to(dev)}, p.to(dev))
+    assert _lean_count() - n0 == 1
+    for k, v in ref.items():
+        assert_close(out[k], v, RTOL_FLUX, f'lean fwd-only:{k}')
+
+
+def test_lean_not_taken_for_other_cotangents(monkeypatch):
+    """A loss on more than the streamflow series goes to K2 and still matches the oracle."""
+    from oracle import hbv_oracle as O
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    T, B = 19, 2400
+    x = O.synthetic_forcing(T, B, seed=45)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(46))
+    pc = p.clone().requires_grad_(True)
+    ref, _ = O.forward_packed('hbv', x, pc, nmul=NMUL, warm_up=0, dynamic_params=D2)
+    (ref['streamflow'].sum() + 0.5 * ref['AET_hydro'].sum()).backward()
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'warm_up': 0, 'dynamic_params': {'Hbv': D2}, 'nmul': NMUL}, device=dev)
+    pg = p.to(dev).requires_grad_(True)
+    n0 = _lean_count()
+    out = m({'x_phy': x.to(dev)}, pg)
+    (out['streamflow'].sum() + 0.5 * out['AET_hydro'].sum()).backward()
+    assert _lean_count() - n0 == 1        # K1s forward, K2 adjoint
+    assert_close(pg.grad, pc.grad, RTOL_GRAD, 'two-series loss: grad')
+
+
+def _split_inputs(B, T, n_static_cols, hourly, seed):
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(seed)
+    x = O.synthetic_forcing(T, B, seed=seed + 1)
+    if hourly:
+        x = x / 24.0
+    p0 = torch.rand(T, B, 3 * NMUL, generator=g).to(dev)
+    p1 = torch.rand(B, n_static_cols, generator=g).to(dev)
+    xd = {'x_phy': x.to(dev), 'ac_all': (torch.rand(B, generator=g) * 5000).to(dev),
+          'elev_all': (torch.rand(B, generator=g) * 3500).to(dev)}
+    return xd, p0, p1
+
+
+@pytest.mark.parametrize('B', [2500, 2501])
+def test_lean_hbv_2_matches_k1_k2(B, monkeypatch):
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    xd, p0, p1 = _split_inputs(B, 26, 13 * NMUL + 2, False, 51)
+
+    def run(lean):
+        monkeypatch.setenv('HBV_B200_LEAN', '1' if lean else '0')
+        M = hydrodl2.load_model('hbv_2', ver_name='Hbv_2')
+        m = M({'dynamic_params': {'Hbv_2': D3}, 'nmul': NMUL, 'warm_up': 0, 'state_series': False}, device=dev)
+        ps = [q.detach().clone().requires_grad_(True) for q in (p0, p1)]
+        n0 = _lean_count()
+        out = m(xd, ps)
+        out['streamflow'].sum().backward()
+        torch.cuda.synchronize()
+        return out, [q.grad for q in ps], _lean_count() - n0
+
+    out1, g1, n1 = run(True)
+    out0, g0, n0 = run(False)
+    assert (n1, n0) == (2, 0)
+    for k in out0:
+        assert_close(out1[k], out0[k], 1e-6, f'hbv_2 lean vs K1 B={B}:{k}')
+    for a, b, n in zip(g1, g0, ('dyn', 'static')):
+        assert_close(a, b, 1e-6, f'hbv_2 lean vs K2 B={B}:grad {n}')
+
+
+def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    xd, p0, p1 = _split_inputs(2520, 50, 16 * NMUL, True, 61)
+
+    def run(lean):
+        monkeypatch.setenv('HBV_B200_LEAN', '1' if lean else '0')
+        M = hydrodl2.load_model('hbv_2_hourly', ver_name='Hbv_2_hourly')
+        m = M({'dynamic_params': {'Hbv_2_hourly': D3}, 'nmul': NMUL, 'routing': False, 'state_series': False}, device=dev)
+        m.use_distr_routing = False
+        ps = [q.detach().clone().requires_grad_(True) for q in (p0, p1)]
+        n0 = _lean_count()
+        out = m(xd, ps)
+        out['Qs'].sum().backward()
+        torch.cuda.synchronize()
+        return out, [q.grad for q in ps], _lean_count() - n0
+
+    out1, g1, n1 = run(True)
+    out0, g0, n0 = run(False)
+    assert (n1, n0) == (2, 0)
+    assert_close(out1['Qs'], out0['Qs'], 1e-6, 'hourly lean vs K1: Qs')
+    for a, b, n in zip(g1, g0, ('dyn', 'static')):
+        assert_close(a, b, 1e-6, f'hourly lean vs K2: grad {n}')
