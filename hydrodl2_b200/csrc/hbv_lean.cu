@@ -31,7 +31,8 @@
 namespace hbv {
 
 constexpr int LNM = 16;      // components per basin
-constexpr int LBPB = 8;      // basins per CTA (128 threads)
+// basins per CTA (template LBPB): 8 (128 threads) on large grids; 2 (one warp, so the chunk barrier
+// costs nothing and the CTAs spread over all SMs) on small, latency-bound ones
 constexpr int LTC = 4;       // forward: time steps per output chunk
 
 template <int NPAR, int DM, int LAYOUT>
@@ -64,8 +65,8 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // ================================================================================================
 // K1s: forward.  CK: store the state before every step (K = 1) for the adjoint.
 // ================================================================================================
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK>
-__global__ void __launch_bounds__(128, 6)
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB>
+__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
@@ -118,7 +119,7 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     constexpr int tstride_s = LBPB * bstride;
     float* const my_slot = tile + bl * bstride + j * NFP;
     constexpr float inv_nmul = 1.0f / (float)LNM;
-    constexpr int items = LTC * LBPB * 3;            // 96 <= 128 threads
+    constexpr int items = LTC * LBPB * 3;            // 96 <= 128 threads (24 <= 32)
     const int r_q = tid % 3;
     const int r_r = tid / 3;
     const int r_bl = r_r % LBPB;
@@ -186,8 +187,10 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // ================================================================================================
 // K2s: adjoint, every state stored (K = 1), upstream gradient on the streamflow series
 // ================================================================================================
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
-__global__ void __launch_bounds__(128, 4)
+// PF: input prefetch distance in time steps (register buffers, the loop is unrolled PF times):
+// 1 where many resident warps hide HBM latency, 3 on small grids where one warp owns a scheduler
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF>
+__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
 hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
@@ -243,13 +246,16 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     };
 
     Tape tp;
-    In nxt;
-    load(nxt);
-#pragma unroll 1
-    for (int t = d.T - 1; t >= 0; --t) {
-        const In cur = nxt;
-        if (t > 0) load(nxt);
+    In buf[PF];
+    int t_load = d.T - 1;
+    auto load_next = [&](In& in) {
+        if (t_load >= 0) load(in);
+        --t_load;
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) load_next(buf[u]);
 
+    auto process = [&](const In& cur) {
         float dpd[ND];
 #pragma unroll
         for (int i = 0; i < NPAR; ++i)
@@ -279,6 +285,17 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
             else gacc[i] += gp[i];
         }
         pg -= sd;
+    };
+#pragma unroll 1
+    for (int t = d.T - 1; t >= 0; t -= PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (t - u >= 0) {
+                const In cur = buf[u];
+                load_next(buf[u]);
+                process(cur);
+            }
+        }
     }
 
     // static parameters: d(par)/d(raw) recomputed here, written once (as in hbv_bwd.cu)
@@ -316,19 +333,19 @@ static bool lean_common_ok(const KDesc& d) {
     const char* e = std::getenv("HBV_B200_LEAN");        // 0: always K1 / K2 (A/B experiments)
     if (e && e[0] == '0') return false;
     if (d.nmul != LNM || d.nvar != 3 || d.i_prcp != 0 || d.i_tmean != 1 || d.i_pet != 2) return false;
-    // throughput regime only: the small-grid regime keeps the cp.async ring kernels
-    const char* force = std::getenv("HBV_B200_RING");
-    if (force) return force[0] == '0';
-    return (long long)d.B * LNM > 148LL * 4 * 32 * 2;
+    const char* force = std::getenv("HBV_B200_RING");    // 1: keep the cp.async ring kernels (A/B)
+    return !(force && force[0] == '1');
 }
 
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
-static int launch_fwd_lean(KDesc d, const FwdPtrs& io, cudaStream_t st) {
+static bool lean_small_grid(const KDesc& d) { return (long long)d.B * LNM <= 148LL * 4 * 32 * 2; }
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB>
+static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     d.BPB = LBPB;
     const size_t smem = (size_t)LTC * LBPB * (LNM * NFP + 12) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB><<<grid, LBPB * LNM, smem, st>>>(d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -337,15 +354,27 @@ static int launch_fwd_lean(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 }
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
-static int launch_bwd_lean(KDesc d, const BwdPtrs& io, cudaStream_t st) {
+static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
+    return lean_small_grid(d) ? launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2>(d, io, st)
+                              : launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8>(d, io, st);
+}
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF>
+static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     d.BPB = LBPB;
     const int grid = (d.B + LBPB - 1) / LBPB;
-    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG><<<grid, LBPB * LNM, 0, st>>>(d, io);
+    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF><<<grid, LBPB * LNM, 0, st>>>(d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) set_error(cudaGetErrorString(e));
     return (int)e;
+}
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
+static int launch_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
+    return lean_small_grid(d) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 3>(d, io, st)
+                              : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1>(d, io, st);
 }
 
 template <int VAR, bool BETAET, int DM>
