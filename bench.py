@@ -549,7 +549,7 @@ def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_ste
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--workload', choices=list(WORKLOADS), default='c2')

@@ -65,7 +65,12 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // ================================================================================================
 // K1s: forward.  CK: store the state before every step (K = 1) for the adjoint.
 // ================================================================================================
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB>
+// RD: 0 = inputs prefetched into registers (large grids: many resident warps hide HBM latency);
+// > 0 = per-thread shared-memory ring of RD steps filled with cp.async (small grids: one warp owns
+// a scheduler, only prefetch DISTANCE hides latency, and register loads cannot provide it — loads
+// in flight share the warp's six scoreboard slots, so waiting for the oldest waits for younger
+// ones too; ncu showed 55-64 % of all stall samples on the first use of a prefetched register)
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     using TR = Traits<VAR>;
@@ -149,18 +154,57 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         o4[2] = make_float4(F[8], F[9], F[10], TR::NFLUX > 11 ? F[11] : 0.f);
     };
 
-    // two named prefetch buffers of two steps each (see hbv_fwd.cu: loads in flight must not
-    // share a scoreboard slot with the values being consumed)
+    // ring (RD > 0): [step][thread][NSP] after the output tile; a thread only touches its own slots
+    constexpr int NSP = (3 + ND) | 1;
+    constexpr int RDS = RD > 0 ? RD : 2;
+    float* const ring0 = tile + LTC * tstride_s + tid * NSP;
+    constexpr int step_floats = LBPB * LNM * NSP;
+    float* const ring_end = ring0 + RDS * step_floats;
+    float* wp = ring0;
+    const float* rp = ring0;
+    auto issue = [&]() {             // stage the next time step (the last row again past the end)
+        cp_async4(wp + 0, pf); cp_async4(wp + 1, pf + 1); cp_async4(wp + 2, pf + 2);
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0)) cp_async4(wp + 3 + DS::slot(i), pd + lean_col<NPAR, DM, LAYOUT>(i));
+        cp_async_commit();
+        if (++t_issue < d.T) { pf += sf; pd += sd; }
+        wp += step_floats;
+        if (wp == ring_end) wp = ring0;
+    };
+    auto pop = [&](In& in) {         // oldest staged step
+        cp_async_wait<RDS - 2>();
+        issue();
+        in.P = rp[0]; in.T = rp[1]; in.E = rp[2];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) in.raw[k] = rp[3 + k];
+        rp += step_floats;
+        if (rp == ring_end) rp = ring0;
+    };
+
+    // registers (RD == 0): two named prefetch buffers of two steps each (see hbv_fwd.cu: loads in
+    // flight must not share a scoreboard slot with the values being consumed)
     In A0, A1, B0, B1;
-    load(A0); load(A1);
+    if constexpr (RD > 0) {
+#pragma unroll 1
+        for (int q = 0; q < RDS - 1; ++q) issue();
+    } else {
+        load(A0); load(A1);
+    }
     for (int t0 = 0; t0 < d.T; t0 += LTC) {
         const int tcn = min(LTC, d.T - t0);
-        load(B0); load(B1);
-        do_step(A0, 0);
-        if (1 < tcn) do_step(A1, 1);
-        load(A0); load(A1);
-        if (2 < tcn) do_step(B0, 2);
-        if (3 < tcn) do_step(B1, 3);
+        if constexpr (RD > 0) {
+#pragma unroll
+            for (int u = 0; u < LTC; ++u)
+                if (u < tcn) { pop(A0); do_step(A0, u); }
+        } else {
+            load(B0); load(B1);
+            do_step(A0, 0);
+            if (1 < tcn) do_step(A1, 1);
+            load(A0); load(A1);
+            if (2 < tcn) do_step(B0, 2);
+            if (3 < tcn) do_step(B1, 3);
+        }
         __syncthreads();
         if (r_ok && r_tc < tcn) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,6 +222,7 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         r_o += r_adv;
         __syncthreads();
     }
+    if constexpr (RD > 0) cp_async_wait<0>();
     if (valid && io.state_out != nullptr) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) io.state_out[s * nlane + lane] = S[s];
@@ -189,7 +234,8 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // ================================================================================================
 // PF: input prefetch distance in time steps (register buffers, the loop is unrolled PF times):
 // 1 where many resident warps hide HBM latency, 3 on small grids where one warp owns a scheduler
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF>
+// RD as in the forward kernel (0: registers, PF steps ahead; > 0: cp.async ring of RD steps)
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
 hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     using TR = Traits<VAR>;
@@ -245,6 +291,43 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         pf -= sf; pd -= sd; pq -= d.B;
     };
 
+    extern __shared__ __align__(16) float ringmem[];
+    constexpr int NSP = (4 + ND + 5) | 1;
+    constexpr int RDS = RD > 0 ? RD : 2;
+    float* const ring0 = ringmem + tid * NSP;
+    constexpr int step_floats = LBPB * LNM * NSP;
+    float* const ring_end = ring0 + RDS * step_floats;
+    float* wp = ring0;
+    const float* rp = ring0;
+    int t_stage = d.T - 1;
+    auto issue = [&]() {             // stage the inputs of the next step of the sweep (if any)
+        if (t_stage >= 0) {
+            cp_async4(wp + 0, pf); cp_async4(wp + 1, pf + 1); cp_async4(wp + 2, pf + 2);
+            cp_async4(wp + 3, pq);
+#pragma unroll
+            for (int i = 0; i < NPAR; ++i)
+                if (DS::is_dyn(i, 0)) cp_async4(wp + 4 + DS::slot(i), pd + lean_col<NPAR, DM, LAYOUT>(i));
+#pragma unroll
+            for (int s = 4; s >= 0; --s) { pc -= nlane; cp_async4(wp + 4 + ND + s, pc); }
+            pf -= sf; pd -= sd; pq -= d.B;
+        }
+        --t_stage;
+        cp_async_commit();
+        wp += step_floats;
+        if (wp == ring_end) wp = ring0;
+    };
+    auto pop = [&](In& in) {
+        cp_async_wait<RDS - 2>();
+        issue();
+        in.P = rp[0]; in.T = rp[1]; in.E = rp[2]; in.q = rp[3];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) in.raw[k] = rp[4 + k];
+#pragma unroll
+        for (int s2 = 0; s2 < 5; ++s2) in.S[s2] = rp[4 + ND + s2];
+        rp += step_floats;
+        if (rp == ring_end) rp = ring0;
+    };
+
     Tape tp;
     In buf[PF];
     int t_load = d.T - 1;
@@ -252,8 +335,13 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         if (t_load >= 0) load(in);
         --t_load;
     };
+    if constexpr (RD > 0) {
+#pragma unroll 1
+        for (int q = 0; q < RDS - 1; ++q) issue();
+    } else {
 #pragma unroll
-    for (int u = 0; u < PF; ++u) load_next(buf[u]);
+        for (int u = 0; u < PF; ++u) load_next(buf[u]);
+    }
 
     auto process = [&](const In& cur) {
         float dpd[ND];
@@ -286,14 +374,23 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         }
         pg -= sd;
     };
+    if constexpr (RD > 0) {
 #pragma unroll 1
-    for (int t = d.T - 1; t >= 0; t -= PF) {
+        for (int t = d.T - 1; t >= 0; --t) {
+            pop(buf[0]);
+            process(buf[0]);
+        }
+        cp_async_wait<0>();
+    } else {
+#pragma unroll 1
+        for (int t = d.T - 1; t >= 0; t -= PF) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            if (t - u >= 0) {
-                const In cur = buf[u];
-                load_next(buf[u]);
-                process(cur);
+            for (int u = 0; u < PF; ++u) {
+                if (t - u >= 0) {
+                    const In cur = buf[u];
+                    load_next(buf[u]);
+                    process(cur);
+                }
             }
         }
     }
@@ -337,15 +434,38 @@ static bool lean_common_ok(const KDesc& d) {
     return !(force && force[0] == '1');
 }
 
-static bool lean_small_grid(const KDesc& d) { return (long long)d.B * LNM <= 148LL * 4 * 32 * 2; }
+// Which form runs where (measured on B200, `hbv` D2 fwd+bwd, ms per kernel):
+//   basins        531     2,500    5,000    10,000   22,500
+//   K1s ring      0.24    0.79     1.46     2.51     3.61      one-warp CTAs + cp.async ring
+//   K1s regs      0.30    0.69     1.19     2.23     2.54      128-thread CTAs + register prefetch
+//   K2s ring      0.22    0.50     1.00     1.78     3.90
+//   K2s regs      0.43    0.70     1.44     2.32     4.24
+// -> forward: ring form up to 2 warps per scheduler (37,888 lanes), register form above;
+//    adjoint: ring form everywhere (its step is long enough that prefetch distance, not the
+//    LDGSTS + LDS instruction overhead, decides).  HBV_B200_LEAN_SMALL (lanes) and
+//    HBV_B200_LEAN_BWD_RING (0/1) override for experiments.
+static bool lean_small_grid(const KDesc& d) {
+    long long thr = 148LL * 4 * 32 * 2;
+    if (const char* e = std::getenv("HBV_B200_LEAN_SMALL")) thr = std::atoll(e);
+    return (long long)d.B * LNM <= thr;
+}
+static bool lean_bwd_ring(const KDesc& d) {
+    (void)d;
+    const char* e = std::getenv("HBV_B200_LEAN_BWD_RING");
+    return !(e && e[0] == '0');
+}
 
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB>
+constexpr int LRD_F = 12;    // small grids: forward ring depth (steps)
+constexpr int LRD_B = 8;     // small grids: adjoint ring depth
+
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int RD>
 static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
+    constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
-    const size_t smem = (size_t)LTC * LBPB * (LNM * NFP + 12) * sizeof(float);
+    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)RD * LBPB * LNM * ((3 + ND) | 1)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -355,15 +475,17 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
-    return lean_small_grid(d) ? launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2>(d, io, st)
-                              : launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8>(d, io, st);
+    return lean_small_grid(d) ? launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st)
+                              : launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF>
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD>
 static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
+    constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
+    const size_t smem = (size_t)RD * LBPB * LNM * ((4 + ND + 5) | 1) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF><<<grid, LBPB * LNM, 0, st>>>(d, io);
+    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -373,8 +495,8 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
-    return lean_small_grid(d) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 3>(d, io, st)
-                              : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1>(d, io, st);
+    return lean_bwd_ring(d) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 1, LRD_B>(d, io, st)
+                              : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1, 0>(d, io, st);
 }
 
 template <int VAR, bool BETAET, int DM>

@@ -20,7 +20,7 @@ from typing import Any, Optional, Union
 import torch
 
 from ... import _cabi as A
-from ...ops import RunSpec, hbv_run, hbv_states_only
+from ...ops import RunSpec, hbv_run, hbv_states_only, start_grad_plane
 
 _FLUX_KEYS = (
     # (dict key, source) — source: ('r', i) routed plane i, ('f', slot) flux slot, 'pet'
@@ -205,16 +205,19 @@ class PackedHbv(torch.nn.Module):
 
         parameters = parameters.contiguous()
         x = x.contiguous()
+        spec = self._spec(self.dynamic_params, self.routing)
+        gplane = None
         if warm_up > 0:
+            # the dense gradient plane starts zeroing while the warm-up kernel runs
+            gplane = start_grad_plane(spec, parameters)
             with torch.no_grad():
                 spec_w = self._spec(dyn_names=(), routing=False)
                 current = hbv_states_only(spec_w, x[:warm_up], parameters[:warm_up].detach(),
                                           None, current)
 
         drop = self._draw_drop(ngrid)
-        spec = self._spec(self.dynamic_params, self.routing)
         res = hbv_run(spec, x[warm_up:], parameters, None, current, drop=drop,
-                      muwts=self.muwts, t_off=warm_up)
+                      muwts=self.muwts, t_off=warm_up, gplane=gplane)
 
         states = tuple(res['state_out'][i] for i in range(5))
         self._states_cache = [s.detach() for s in states]

@@ -47,6 +47,7 @@ def _fused_zero_fill(spec, dyn_ncol) -> bool:
     return 2 * n_dyn * spec.nmul >= dyn_ncol
 
 _SIDE_STREAMS = {}
+_SMALL_GRID_LANES = 148 * 4 * 32 * 2      # same boundary as the kernels' small-grid regime
 
 
 def _side_stream(dev):
@@ -187,11 +188,41 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
     return state_out
 
 
+def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], _checked: bool = False):
+    """Allocate the dense gradient plane of `dyn` and start zeroing it on the side stream right
+    away.  A model with a warm-up run calls this BEFORE the warm-up kernel, so the memset shares
+    the device with a kernel that moves almost no HBM bytes instead of with K1 (C2: 489 MB of
+    zeros against an 88 us warm-up).  Returns (plane, event) for `hbv_run(gplane=...)`, or None
+    when no plane is needed (no gradient, or the adjoint writes every element itself)."""
+    if not _checked:      # (_HbvRun.forward has made these checks itself; grad mode is off in there)
+        if dyn is None or not dyn.is_cuda or not (torch.is_grad_enabled() and dyn.requires_grad):
+            return None
+        if _fused_zero_fill(spec, dyn.shape[-1]):
+            return None
+    dev = dyn.device
+    gbuf = torch.empty_like(dyn)
+    if dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES:
+        # Latency-bound regime (a warp or two per scheduler): a full-occupancy fill running next to
+        # the recurrence kernels starves them for longer than the fill itself takes (C2: a 76 us
+        # memset stretched the 88 us warm-up kernel to 275 us) — zero in stream order instead.
+        gbuf.zero_()
+        return gbuf, None
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        gbuf.zero_()
+        gev = torch.cuda.Event()
+        gev.record(side)
+    return gbuf, gev
+
+
 class _HbvRun(torch.autograd.Function):
     """K1 + K4 forward, K4^T + K2 backward."""
 
     @staticmethod
-    def forward(ctx, spec: RunSpec, forcing, dyn, sta, state_in, drop, attrs, muwts, t_off):
+    def forward(ctx, spec: RunSpec, forcing, dyn, sta, state_in, drop, attrs, muwts, t_off, gplane=None,
+                track=True):
         # `dyn` is the FULL dynamic/packed tensor; rows [t_off:] belong to this run.
         lib = A.load()
         dev = forcing.device
@@ -202,7 +233,9 @@ class _HbvRun(torch.autograd.Function):
         sta_ncol = 0 if sta is None else sta.shape[-1]
         mu, mu_ts = _prep_muwts(muwts, T, B, nmul, dev)
         d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
-        need_grad = any(t is not None and t.requires_grad for t in (dyn, sta, state_in, forcing, muwts))
+        # `track`: grad mode of the caller (inside an autograd.Function it is always off, and a leaf
+        # keeps requires_grad=True under no_grad): inference must not pay for stored states
+        need_grad = track and any(t is not None and t.requires_grad for t in (dyn, sta, state_in, forcing, muwts))
         K = spec.ckpt_interval or int(lib.hbv_b200_auto_ckpt(T, B, nmul))   # 0 = auto
         d.ckpt_interval = K
         nseg = (T + K - 1) // K
@@ -213,14 +246,10 @@ class _HbvRun(torch.autograd.Function):
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
         gbuf = gev = None
         if need_grad and dyn is not None and dyn.requires_grad and not _fused_zero_fill(spec, dyn_ncol):
-            cur = torch.cuda.current_stream(dev)
-            side = _side_stream(dev)
-            gbuf = torch.empty_like(dyn)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                gbuf.zero_()
-                gev = torch.cuda.Event()
-                gev.record(side)
+            if gplane is not None:
+                gbuf, gev = gplane            # started earlier (start_grad_plane)
+            else:
+                gbuf, gev = start_grad_plane(spec, dyn, _checked=True)
 
         flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
         state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
@@ -305,7 +334,8 @@ class _HbvRun(torch.autograd.Function):
         if dyn is not None:
             if ctx.gbuf is not None:
                 gdyn_full, ctx.gbuf = ctx.gbuf, None
-                torch.cuda.current_stream(dev).wait_event(ctx.gev)
+                if ctx.gev is not None:
+                    torch.cuda.current_stream(dev).wait_event(ctx.gev)
             elif _fused_zero_fill(spec, dyn_ncol):
                 zero_fill = 1
                 gdyn_full = torch.empty_like(dyn)
@@ -387,11 +417,11 @@ class _HbvRun(torch.autograd.Function):
             gmu = gmu.view((-1, B, nmul) if mu_ts else (1, B, nmul)).sum_to_size(ctx.muwts_shape)
         if not (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
             gdyn_full = gsta = None
-        return (None, gforcing, gdyn_full, gsta, gstate_in, None, None, gmu, None)
+        return (None, gforcing, gdyn_full, gsta, gstate_in, None, None, gmu, None, None, None)
 
 
 def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, muwts=None,
-            t_off: int = 0):
+            t_off: int = 0, gplane=None):
     """Run the recurrence (+ routing) on rows [t_off:] of `dyn`.
 
     forcing  [T, B, nvar]  (already sliced to the run)
@@ -408,7 +438,8 @@ def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, m
     if sta is not None:
         _check_cuda(sta, 'static parameters')
         sta = sta.contiguous()
-    outs = _HbvRun.apply(spec, forcing, dyn, sta, state_in.contiguous(), drop, attrs, muwts, t_off)
+    outs = _HbvRun.apply(spec, forcing, dyn, sta, state_in.contiguous(), drop, attrs, muwts, t_off, gplane,
+                         torch.is_grad_enabled())
     nf = spec.nflux
     n_r = spec.n_routed if spec.routing else 0
     return {
@@ -431,14 +462,14 @@ class _HbvAdjRun(torch.autograd.Function):
               `parameters`, written in place by the kernels."""
 
     @staticmethod
-    def forward(ctx, spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop, warm_up, newton):
+    def forward(ctx, spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop, warm_up, newton, track=True):
         lib = A.load()
         dev = forcing.device
         Tt, B, nvar = forcing.shape
         nmul, ncol = spec.nmul, dyn.shape[-1]
         T = Tt - warm_up
         tol, maxu = newton
-        need_grad = dyn.requires_grad or state_in.requires_grad
+        need_grad = track and (dyn.requires_grad or state_in.requires_grad)
         stream = _stream(dev)
         stats = torch.zeros(2, dtype=torch.int32, device=dev)
 
@@ -539,7 +570,7 @@ class _HbvAdjRun(torch.autograd.Function):
                 io.gdyn, io.gstate_in = _ptr(gdyn), _ptr(gstate_in)
                 with _timed('hbv_adj_bwd_warmup', dev):
                     A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec_w, warm_up)), C.byref(io), stream), 'adj_bwd(warm-up)')
-        return (None, None, None, gdyn, gstate_in if state_in.requires_grad else None, None, None, None)
+        return (None, None, None, gdyn, gstate_in if state_in.requires_grad else None, None, None, None, None)
 
 
 def hbv_adj_run(spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop=None, warm_up: int = 0,
@@ -552,6 +583,6 @@ def hbv_adj_run(spec_w: RunSpec, spec: RunSpec, forcing, dyn, state_in, drop=Non
     _check_cuda(dyn, 'parameters')
     qsim, routed, state_out, stats = _HbvAdjRun.apply(
         spec_w, spec, forcing.contiguous(), dyn.contiguous(), state_in.contiguous(), drop,
-        int(warm_up), (tol, max_updates))
+        int(warm_up), (tol, max_updates), torch.is_grad_enabled())
     return {'qsim': qsim, 'routed': routed if spec.routing else None, 'state_out': state_out,
             'stats': stats}

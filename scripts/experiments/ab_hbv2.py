@@ -4,7 +4,7 @@ size, for A/B runs of the input path (HBV_B200_DENSE=0/1):  python scripts/ab_hb
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import hydrodl2_b200 as hydrodl2  # noqa: E402

@@ -8,7 +8,7 @@ import json
 d=json.load(open('gpurun_out/lean_$l.json'))
 print('shard lean=$l', 'ms %.3f fwd-only %.3f' % (d['ms_per_step'], d['fwd']['ms_per_step']), {k: round(v, 3) for k, v in d['kernel_ms'].items()})
 PY
-HBV_B200_LEAN=$l timeout 200 python scripts/ab_hbv2.py 22500 730 2>&1 | tail -1
+HBV_B200_LEAN=$l timeout 200 python scripts/experiments/ab_hbv2.py 22500 730 2>&1 | tail -1
 HBV_B200_LEAN=$l timeout 300 python scripts/bench_configs.py c4 --steps 3 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
