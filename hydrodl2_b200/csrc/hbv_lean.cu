@@ -440,6 +440,7 @@ static bool lean_common_ok(const KDesc& d) {
 //   K1s regs      0.30    0.69     1.19     2.23     2.54      128-thread CTAs + register prefetch
 //   K2s ring      0.22    0.50     1.00     1.78     3.90
 //   K2s regs      0.43    0.70     1.44     2.32     4.24
+// (a ring with 128-thread CTAs was also tried for the forward at 22,500 basins: 2.95 vs 1.43 ms)
 // -> forward: ring form up to 2 warps per scheduler (37,888 lanes), register form above;
 //    adjoint: ring form everywhere (its step is long enough that prefetch distance, not the
 //    LDGSTS + LDS instruction overhead, decides).  HBV_B200_LEAN_SMALL (lanes) and
@@ -475,8 +476,8 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
-    return lean_small_grid(d) ? launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st)
-                              : launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
+    if (lean_small_grid(d)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
+    return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD>
