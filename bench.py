@@ -165,9 +165,22 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(inside)}
 
 
+def synthetic_forcing(T, B, seed):
+    """[T, B, 3] = (prcp, tmean, pet) on the CPU: seasonal temperature crossing
+    the snow threshold, 50 % dry days, seasonal PET.  (bench.py's own generator: the B200 arm does
+    not import anything from oracle/.)"""
+    g = torch.Generator().manual_seed(seed)
+    d = torch.arange(T, dtype=torch.float32).view(T, 1)
+    ob = torch.rand(1, B, generator=g) * 16 - 8
+    season = torch.sin(2 * math.pi * (d - 110) / 365)
+    tmean = 5 + 12 * season + ob + 4 * torch.randn(T, B, generator=g)
+    prcp = 5 * torch.relu(torch.randn(T, B, generator=g))
+    pet = torch.relu(2 + 2 * season) + 0.5 * torch.rand(T, B, generator=g)
+    return torch.stack([prcp, tmean, pet], dim=-1).contiguous()
+
+
 def make_inputs(wl, B, seed, device=None, pin=False):
     """Synthetic forcings + raw parameters ~ N(0,1)."""
-    from oracle.hbv_oracle import synthetic_forcing  # input generator only
     T = wl['warm_up'] + wl['T']
     ncol = wl['n_par'] * NMUL + 2
     if device is not None and B > 4096:

@@ -276,8 +276,9 @@ hbv_fwd_dense_kernel(const KDesc d, const FwdPtrs io) {
 // ================================================================================================
 // K2d: adjoint (every state stored, K = 1)
 // ================================================================================================
-template <int VAR, bool BETAET, int DM, int LAYOUT>
-__global__ void __launch_bounds__(128, 4)
+// MINB: resident CTAs per SM the register allocation is sized for (4: <= 128 registers, 5: <= 96)
+template <int VAR, bool BETAET, int DM, int LAYOUT, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 hbv_bwd_dense_kernel(const KDesc d, const BwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
@@ -601,10 +602,9 @@ static int launch_fwd_dense(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     return (int)e;
 }
 
-template <int VAR, bool BETAET, int DM, int LAYOUT>
-static int launch_bwd_dense(KDesc d, const BwdPtrs& io, cudaStream_t st) {
-    d.BPB = env_int("HBV_B200_DENSE_BPB", 128 / DNM);
-    if (d.BPB != 2 && d.BPB != 4 && d.BPB != 8) d.BPB = 128 / DNM;
+template <int VAR, bool BETAET, int DM, int LAYOUT, int MINB>
+static int launch_bwd_dense_m(KDesc d, const BwdPtrs& io, cudaStream_t st) {
+    d.BPB = 128 / DNM;
     d.slack = run_slack(d, io.dyn, io.forcing, io.gdyn, io.gflux[HBV_F_QSIM]);
     const DenseGeom g = dense_geom(d);
     const size_t fixed = 64 + 2 * (size_t)g.obytes;
@@ -612,12 +612,12 @@ static int launch_bwd_dense(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     int ns = env_int("HBV_B200_DENSE_NS_BWD", 0);
     if (ns <= 0) {
         ns = 6;
-        const size_t budget = ((size_t)(227 * 1024) / (4 * (128 / DNM) / d.BPB)) - 1024;   // 16 warps / SM
+        const size_t budget = (size_t)(227 * 1024) / MINB - 1024;
         while (ns > 2 && fixed + ns * slot > budget) --ns;
     }
     if (ns < 2 || ns > 8 || fixed + ns * slot > 200 * 1024) return HBV_NOT_ELIGIBLE;
     d.nstage = ns;
-    auto k = hbv_bwd_dense_kernel<VAR, BETAET, DM, LAYOUT>;
+    auto k = hbv_bwd_dense_kernel<VAR, BETAET, DM, LAYOUT, MINB>;
     static std::atomic<int> optin[HBV_MAX_DEVICES];
     int rc = optin_smem(k, fixed + ns * slot, optin);
     if (rc) return rc;
@@ -628,6 +628,14 @@ static int launch_bwd_dense(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) set_error(cudaGetErrorString(e));
     return (int)e;
+}
+
+template <int VAR, bool BETAET, int DM, int LAYOUT>
+static int launch_bwd_dense(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
+    const int m = env_int("HBV_B200_DENSE_MINB", 5);
+    if (m == 6) return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 6>(d, io, st);
+    if (m == 4) return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 4>(d, io, st);
+    return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 5>(d, io, st);
 }
 
 // Try the dense forward.  Returns HBV_NOT_ELIGIBLE when the call is not eligible (the caller then takes K1).
