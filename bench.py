@@ -571,8 +571,11 @@ def main():
                     help='checkpoint interval of the adjoint (0 = library default: 1 for small problems, else 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')
-    ap.add_argument('--graph', action='store_true',
-                    help='time a CUDA-graph replay of the step (single GPU; measured no faster than eager)')
+    ap.add_argument('--no-graph', dest='graph', action='store_false',
+                    help='time the eager step instead of a CUDA-graph replay of it (single GPU: the step '
+                         'is ~0.55 ms of kernels, about what one eager Python step costs the host, so the '
+                         'eager number depends on the host CPU; multi-GPU runs are always eager)')
+    ap.set_defaults(graph=True)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     # stdout carries exactly one JSON line: while the run is in progress file descriptor 1 points at

@@ -301,6 +301,8 @@ template <int VAR, bool BETAET, int DM>
 int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st);
 template <int VAR, bool BETAET, int DM>
 int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
+template <int VAR, bool BETAET>
+int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st);
 
 void set_error(const char* msg);
 void count_launch(int n = 1);

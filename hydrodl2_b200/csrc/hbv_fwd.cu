@@ -278,7 +278,10 @@ template <int VAR, bool BETAET>
 static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st) {
     const int dm = static_dynmask(d, io.drop != nullptr);
     if (!write_flux) {
-        if (dm == 0) return launch_fwd_k<VAR, BETAET, false, 0>(d, io, st);
+        if (dm == 0) {
+            const int rc = try_fwd_lean_warm<VAR, BETAET>(d, io, st);              // hbv_lean.cu
+            return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, false, 0>(d, io, st);
+        }
         return launch_fwd_k<VAR, BETAET, false, -1>(d, io, st);
     }
     if (dm == 0) return launch_fwd_k<VAR, BETAET, true, 0>(d, io, st);

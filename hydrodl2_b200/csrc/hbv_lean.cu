@@ -70,13 +70,14 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // a scheduler, only prefetch DISTANCE hides latency, and register loads cannot provide it — loads
 // in flight share the warp's six scoreboard slots, so waiting for the oldest waits for younger
 // ones too; ncu showed 55-64 % of all stall samples on the first use of a prefetched register)
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD>
+// WF: write the flux planes (false: the warm-up / `initialize` run — states only, hbv.py:327-346)
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
-    constexpr int ND = DS::NDYN;
+    constexpr int ND = DS::NDYN > 0 ? DS::NDYN : 1;     // (array extent; no slot is used when DM = 0)
     extern __shared__ __align__(16) float tile[];
 
     const int tid = threadIdx.x;
@@ -148,16 +149,18 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
         float F[HBV_MAX_FLUX];
         step_fwd<VAR, BETAET, false>(S, p, P, in.T, PET, lc, F, tp);
-        float4* o4 = reinterpret_cast<float4*>(my_slot + tc * tstride_s);
-        o4[0] = make_float4(F[0], F[1], F[2], F[3]);
-        o4[1] = make_float4(F[4], F[5], F[6], F[7]);
-        o4[2] = make_float4(F[8], F[9], F[10], TR::NFLUX > 11 ? F[11] : 0.f);
+        if constexpr (WF) {
+            float4* o4 = reinterpret_cast<float4*>(my_slot + tc * tstride_s);
+            o4[0] = make_float4(F[0], F[1], F[2], F[3]);
+            o4[1] = make_float4(F[4], F[5], F[6], F[7]);
+            o4[2] = make_float4(F[8], F[9], F[10], TR::NFLUX > 11 ? F[11] : 0.f);
+        }
     };
 
     // ring (RD > 0): [step][thread][NSP] after the output tile; a thread only touches its own slots
-    constexpr int NSP = (3 + ND) | 1;
+    constexpr int NSP = (3 + DS::NDYN) | 1;
     constexpr int RDS = RD > 0 ? RD : 2;
-    float* const ring0 = tile + LTC * tstride_s + tid * NSP;
+    float* const ring0 = tile + (WF ? LTC * tstride_s : 0) + tid * NSP;
     constexpr int step_floats = LBPB * LNM * NSP;
     float* const ring_end = ring0 + RDS * step_floats;
     float* wp = ring0;
@@ -177,7 +180,7 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         issue();
         in.P = rp[0]; in.T = rp[1]; in.E = rp[2];
 #pragma unroll
-        for (int k = 0; k < ND; ++k) in.raw[k] = rp[3 + k];
+        for (int k = 0; k < DS::NDYN; ++k) in.raw[k] = rp[3 + k];
         rp += step_floats;
         if (rp == ring_end) rp = ring0;
     };
@@ -205,6 +208,7 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
             if (2 < tcn) do_step(B0, 2);
             if (3 < tcn) do_step(B1, 3);
         }
+        if constexpr (!WF) continue;
         __syncthreads();
         if (r_ok && r_tc < tcn) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -474,6 +478,29 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     return (int)e;
 }
 
+// warm-up / initialize run: all parameters time-invariant, states only
+template <int VAR, bool BETAET, bool SIG, int LBPB, int RD>
+static int launch_fwd_lean_warm(KDesc d, const FwdPtrs& io, cudaStream_t st) {
+    d.BPB = LBPB;
+    const size_t smem = (size_t)RD * LBPB * LNM * 3 * sizeof(float);
+    const int grid = (d.B + LBPB - 1) / LBPB;
+    hbv_fwd_lean_kernel<VAR, BETAET, 0, 0, SIG, false, LBPB, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    count_launch();
+    count_lean_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+    return (int)e;
+}
+
+template <int VAR, bool BETAET>
+int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
+    if (!lean_common_ok(d) || !lean_small_grid(d)) return HBV_NOT_ELIGIBLE;   // large grids: K1 is as lean
+    if (io.drop != nullptr || io.muwts != nullptr || io.state_series != nullptr || io.ckpt != nullptr)
+        return HBV_NOT_ELIGIBLE;
+    return d.apply_sigmoid ? launch_fwd_lean_warm<VAR, BETAET, true, 2, LRD_F>(d, io, st)
+                           : launch_fwd_lean_warm<VAR, BETAET, false, 2, LRD_F>(d, io, st);
+}
+
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
     if (lean_small_grid(d)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
@@ -542,6 +569,11 @@ template int try_fwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const FwdP
 template int try_fwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_fwd_lean_warm<HBV_VARIANT_HBV, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
+template int try_fwd_lean_warm<HBV_VARIANT_HBV, false>(const KDesc&, const FwdPtrs&, cudaStream_t);
+template int try_fwd_lean_warm<HBV_VARIANT_HBV11P, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
+template int try_fwd_lean_warm<HBV_VARIANT_HBV2, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
+template int try_fwd_lean_warm<HBV_VARIANT_HOURLY, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_bwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);

@@ -10,10 +10,10 @@ gradient memset, and an NCCL all-reduce if there is one) can be captured once an
     out, loss = step.outputs          # static tensors, refreshed by every replay
     step.replay()
 
-Measured on B200 (531 basins): replay is not faster than the eager step (1.45 vs 1.19 ms — the
-side-stream memset branch serialises differently inside a graph), and capturing a step that
-contains an NCCL collective hung on 2 GPUs, so `bench.py` times the eager step; this helper is
-kept for single-GPU inference loops where Python overhead dominates.
+Measured on B200 (531 basins, 0.55 ms of kernels per training step): replay 0.55 ms; the eager
+step 0.57-0.71 ms depending on the box's host CPU (one eager step costs the host about as much as
+the kernels take).  `bench.py` times the replay on one GPU and the eager step on several (capturing
+a step that contains an NCCL collective hung on 2 GPUs).
 
 Inputs must live in static tensors (copy new data into them before `replay()`); the dynamic-
 parameter dropout draw (`dy_drop > 0`, a CPU RNG draw per forward, hbv.py:240-246) would be
