@@ -217,14 +217,18 @@ def bytes_fwd(wl, K=16):
     return 4 * (3 + len(wl['dyn']) * NMUL + wl['nflux']) + 5 * NMUL * 4 / K
 
 
-def bytes_bwd(wl, K=16, n_g=1):
-    # forcings + dynamic parameters + n_g upstream series read, dynamic gradients written,
-    # checkpoints read
-    return 4 * (3 + 2 * len(wl['dyn']) * NMUL + n_g) + 5 * NMUL * 4 / K
+def bytes_bwd(wl, K=16, n_g=1, fused=False):
+    # forcings + dynamic parameters + n_g upstream series + stored states read; gradient written:
+    # the dynamic columns only when the caller pre-zeroed the dense plane (memset), the whole dense
+    # [B, ncol] row — a contract output, zeros included — when the adjoint writes it itself
+    ncol = wl['n_par'] * NMUL + 2
+    n_dyn = len(wl['dyn']) * NMUL
+    written = ncol if fused else n_dyn
+    return 4 * (3 + n_dyn + n_g + written) + 5 * NMUL * 4 / K
 
 
-def per_unit_bytes(wl, K):
-    return {'hbv_bwd': bytes_bwd(wl, K), 'hbv_fwd': bytes_fwd(wl, K), 'hbv_fwd_warmup': 12.0,
+def per_unit_bytes(wl, K, fused=False):
+    return {'hbv_bwd': bytes_bwd(wl, K, fused=fused), 'hbv_fwd': bytes_fwd(wl, K), 'hbv_fwd_warmup': 12.0,
             'route_fwd': 32.0,    # 4 series read + 4 routed series written
             'route_bwd': 12.0}    # streamflow-only loss: read g, read x, write g_in (1 series)
 
@@ -371,9 +375,14 @@ def run_b200(args):
             kms[name] = sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))
         return ms, kms
 
+    def fused_fill(wl, B):     # does the adjoint write the dense gradient rows itself? (ops.py policy)
+        Model = hydrodl2.load_model(wl['model'], ver_name=wl['cls'])
+        spec = Model(model_config(wl), device=dev)._spec(wl['dyn'], True)
+        return bool(ops._fused_zero_fill(spec, wl['n_par'] * NMUL + 2, B))
+
     def roofline_of(wl, B, kms, kernel, traffic_key=None):
         units = B * (wl['T'] if kernel != 'hbv_fwd_warmup' else wl['warm_up'])
-        per_unit = per_unit_bytes(wl, k_eff(wl, B))[kernel]
+        per_unit = per_unit_bytes(wl, k_eff(wl, B), fused_fill(wl, B))[kernel]
         achieved = per_unit * units / (kms[kernel] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -384,6 +393,7 @@ def run_b200(args):
                 traffic = None
         return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'memset + dynamic columns',
                 'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
 
     # ---------------- the bench workload: device-resident throughput + per-kernel roofline -----

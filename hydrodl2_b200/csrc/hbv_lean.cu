@@ -239,9 +239,13 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // PF: input prefetch distance in time steps (register buffers, the loop is unrolled PF times):
 // 1 where many resident warps hide HBM latency, 3 on small grids where one warp owns a scheduler
 // RD as in the forward kernel (0: registers, PF steps ahead; > 0: cp.async ring of RD steps)
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD>
+// ZF (one-warp CTAs only): write every element of the gradient rows 0 .. T-2 — the CTA's rows of a
+// step are one contiguous run; the warp zeroes it with 8 B stores, __syncwarp(), then stores the
+// gradients on top — so the dense plane needs no memset (hbv_bwd_io_t.gdyn_zero_fill).
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
 hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
+    static_assert(!ZF || LBPB == 2, "fused zero fill needs a one-warp CTA");
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
@@ -347,7 +351,23 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         for (int u = 0; u < PF; ++u) load_next(buf[u]);
     }
 
+    // fused zero fill: this CTA's run of row t as float2 (rows are 8 B aligned: ncol is even)
+    const int zb0 = blockIdx.x * LBPB;
+    const int nz2 = ZF ? (min(LBPB, d.B - zb0) * d.dyn_ncol) >> 1 : 0;
+    float2* pz = ZF ? reinterpret_cast<float2*>(io.gdyn + ((int64_t)(d.T - 1) * d.B + zb0) * d.dyn_ncol) + tid : nullptr;
+    const int64_t sd2 = sd >> 1;
+    int t_cur = d.T - 1;
+
     auto process = [&](const In& cur) {
+        if constexpr (ZF) {
+            if (t_cur < d.T - 1) {      // row T-1 also holds the static-parameter and routing gradients
+#pragma unroll 4
+                for (int e = tid; e < nz2; e += LBPB * LNM) pz[e - tid] = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            pz -= sd2;
+            --t_cur;
+        }
         float dpd[ND];
 #pragma unroll
         for (int i = 0; i < NPAR; ++i)
@@ -513,7 +533,14 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     d.BPB = LBPB;
     const size_t smem = (size_t)RD * LBPB * LNM * ((4 + ND + 5) | 1) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    if constexpr (LBPB == 2) {
+        if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol)
+            hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
+        else
+            hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    } else {
+        hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    }
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -549,9 +576,11 @@ int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     if (d.K != 1 || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
     if (io.drop != nullptr || io.muwts != nullptr || io.gmuwts != nullptr || io.gforcing != nullptr ||
         io.gstate_series != nullptr || io.gdyn == nullptr) return HBV_NOT_ELIGIBLE;
-    // the caller asked for every element to be written (gdyn_zero_fill): fine when every column
-    // of `dyn` is a time-varying parameter (split form), otherwise K2's zero-fill path
-    if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol) return HBV_NOT_ELIGIBLE;
+    // the caller asked for every element to be written (gdyn_zero_fill): nothing to do when every
+    // column of `dyn` is a time-varying parameter (split form); otherwise the one-warp form zeroes
+    // its rows itself (even row width: 8 B stores)
+    if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol &&
+        !(lean_bwd_ring(d) && d.dyn_ncol % 2 == 0)) return HBV_NOT_ELIGIBLE;
     if (io.gflux[HBV_F_QSIM] == nullptr) return HBV_NOT_ELIGIBLE;
     for (int f = 1; f < HBV_MAX_FLUX; ++f)
         if (io.gflux[f] != nullptr) return HBV_NOT_ELIGIBLE;

@@ -33,18 +33,26 @@ PROFILE = None
 #   None (auto):     fused when at least half of the columns are time-varying parameters — K2
 #                    overwrites most of the tensor anyway and a memset would double the HBM
 #                    writes of an HBM-bound run (hbv_1_1p all-dynamic: 14.8 GB per step at the
-#                    22.5k-basin shard); side-stream memset otherwise.
+#                    22.5k-basin shard) — and for nmul 16 with an even row width (K2s zeroes its
+#                    rows itself); side-stream memset otherwise.
 #   Environment override for experiments: HBV_B200_FUSED_ZERO=0/1.
 FUSED_ZERO_FILL = {'0': False, '1': True}.get(os.environ.get('HBV_B200_FUSED_ZERO', ''), None)
 
 
-def _fused_zero_fill(spec, dyn_ncol) -> bool:
+def _fused_zero_fill(spec, dyn_ncol, n_basins) -> bool:
     if dyn_ncol > 32 * spec.nmul:      # K2's per-thread zero map covers 32 elements per thread
         return False
     if FUSED_ZERO_FILL is not None:
         return bool(FUSED_ZERO_FILL)
     n_dyn = sum(1 for s in spec.par_src[:spec.n_par] if s == A.SRC_DYN_T)
-    return 2 * n_dyn * spec.nmul >= dyn_ncol
+    if 2 * n_dyn * spec.nmul >= dyn_ncol:
+        return True
+    # nmul 16, even row width: the one-warp adjoint (K2s) zeroes a step's rows with a handful of
+    # 8 B stores before it writes the gradients — cheaper than a memset that competes with the
+    # forward kernels for HBM (22.5k-basin shard) or for the schedulers (531 basins)
+    # (measured: shard step 10.7 -> 9.4 ms; on the 531-basin grid the extra stores sit in the
+    # single warp's critical path and cost more than the in-order memset, 0.57 vs 0.56 ms)
+    return spec.nmul == 16 and dyn_ncol % 2 == 0 and n_basins * spec.nmul > _SMALL_GRID_LANES
 
 _SIDE_STREAMS = {}
 _SMALL_GRID_LANES = 148 * 4 * 32 * 2      # same boundary as the kernels' small-grid regime
@@ -197,7 +205,7 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], _checked: bool 
     if not _checked:      # (_HbvRun.forward has made these checks itself; grad mode is off in there)
         if dyn is None or not dyn.is_cuda or not (torch.is_grad_enabled() and dyn.requires_grad):
             return None
-        if _fused_zero_fill(spec, dyn.shape[-1]):
+        if _fused_zero_fill(spec, dyn.shape[-1], dyn.shape[1]):
             return None
     dev = dyn.device
     gbuf = torch.empty_like(dyn)
@@ -245,7 +253,7 @@ class _HbvRun(torch.autograd.Function):
 
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
         gbuf = gev = None
-        if need_grad and dyn is not None and dyn.requires_grad and not _fused_zero_fill(spec, dyn_ncol):
+        if need_grad and dyn is not None and dyn.requires_grad and not _fused_zero_fill(spec, dyn_ncol, B):
             if gplane is not None:
                 gbuf, gev = gplane            # started earlier (start_grad_plane)
             else:
@@ -336,7 +344,7 @@ class _HbvRun(torch.autograd.Function):
                 gdyn_full, ctx.gbuf = ctx.gbuf, None
                 if ctx.gev is not None:
                     torch.cuda.current_stream(dev).wait_event(ctx.gev)
-            elif _fused_zero_fill(spec, dyn_ncol):
+            elif _fused_zero_fill(spec, dyn_ncol, B):
                 zero_fill = 1
                 gdyn_full = torch.empty_like(dyn)
                 if t_off > 0:

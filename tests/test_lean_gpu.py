@@ -169,3 +169,32 @@ def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
     assert_close(out1['Qs'], out0['Qs'], 1e-6, 'hourly lean vs K1: Qs')
     for a, b, n in zip(g1, g0, ('dyn', 'static')):
         assert_close(a, b, 1e-6, f'hourly lean vs K2: grad {n}')
+
+
+def test_lean_fused_zero_fill_on_poisoned_memory(monkeypatch):
+    """K2s writing every element of the gradient rows itself (one-warp form, gdyn_zero_fill) into
+    uninitialised memory == the memset path, including the untouched warm-up rows / routing
+    columns the host clears."""
+    from oracle import hbv_oracle as O
+    from hydrodl2_b200 import ops
+    dev = torch.device('cuda:0')
+    T, B, warm = 33, 2501, 4
+    x = O.synthetic_forcing(T, B, seed=71)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(72))
+    grads = {}
+    prev = ops.FUSED_ZERO_FILL
+    try:
+        for fused in (False, True):
+            ops.FUSED_ZERO_FILL = fused
+            torch.cuda.empty_cache()
+            junk = torch.empty(T * B * (13 * NMUL + 2) + 4096, device=dev).fill_(float('nan'))
+            del junk                                   # poison the block the plane will reuse
+            n0 = _lean_count()
+            _, g, _ = _run_packed('hbv', 'Hbv', 13, x, p, dev, True, monkeypatch, warm)
+            assert _lean_count() - n0 == 2
+            grads[fused] = g
+    finally:
+        ops.FUSED_ZERO_FILL = prev
+    assert torch.isfinite(grads[True]).all()
+    assert_close(grads[True], grads[False], 1e-7, 'fused zero fill vs memset')
+    assert (grads[True][:warm] == 0).all()
