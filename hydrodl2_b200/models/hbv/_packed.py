@@ -209,7 +209,7 @@ class PackedHbv(torch.nn.Module):
         gplane = None
         if warm_up > 0:
             # the dense gradient plane starts zeroing while the warm-up kernel runs
-            gplane = start_grad_plane(spec, parameters)
+            gplane = start_grad_plane(spec, parameters, warm_up)
             with torch.no_grad():
                 spec_w = self._spec(dyn_names=(), routing=False)
                 current = hbv_states_only(spec_w, x[:warm_up], parameters[:warm_up].detach(),

@@ -196,33 +196,44 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
     return state_out
 
 
-def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], _checked: bool = False):
-    """Allocate the dense gradient plane of `dyn` and start zeroing it on the side stream right
-    away.  A model with a warm-up run calls this BEFORE the warm-up kernel, so the memset shares
-    the device with a kernel that moves almost no HBM bytes instead of with K1 (C2: 489 MB of
-    zeros against an 88 us warm-up).  Returns (plane, event) for `hbv_run(gplane=...)`, or None
-    when no plane is needed (no gradient, or the adjoint writes every element itself)."""
+def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0, _checked: bool = False):
+    """Allocate the dense gradient plane of `dyn` and start zeroing what the adjoint will not write
+    on the side stream right away: everything (memset mode) or, when the adjoint writes its rows
+    itself, the warm-up rows [:t_off] and the routing columns of the last row.  A model with a
+    warm-up run calls this BEFORE the warm-up kernel, which moves almost no HBM bytes, so the fill
+    overlaps it instead of K1 / K2.  Returns (plane, event or None, fused) for
+    `hbv_run(gplane=...)`, or None when there is nothing to prepare."""
     if not _checked:      # (_HbvRun.forward has made these checks itself; grad mode is off in there)
         if dyn is None or not dyn.is_cuda or not (torch.is_grad_enabled() and dyn.requires_grad):
             return None
-        if _fused_zero_fill(spec, dyn.shape[-1], dyn.shape[1]):
-            return None
+    fused = _fused_zero_fill(spec, dyn.shape[-1], dyn.shape[1])
+    if fused and t_off == 0:
+        return None           # only the routing columns of one row: the backward clears them in order
     dev = dyn.device
     gbuf = torch.empty_like(dyn)
+
+    def fill():
+        if fused:
+            gbuf[:t_off].zero_()
+            if spec.n_par * spec.nmul < dyn.shape[-1]:
+                gbuf[dyn.shape[0] - 1, :, spec.n_par * spec.nmul:].zero_()
+        else:
+            gbuf.zero_()
+
     if dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES:
         # Latency-bound regime (a warp or two per scheduler): a full-occupancy fill running next to
         # the recurrence kernels starves them for longer than the fill itself takes (C2: a 76 us
         # memset stretched the 88 us warm-up kernel to 275 us) — zero in stream order instead.
-        gbuf.zero_()
-        return gbuf, None
+        fill()
+        return gbuf, None, fused
     cur = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
-        gbuf.zero_()
+        fill()
         gev = torch.cuda.Event()
         gev.record(side)
-    return gbuf, gev
+    return gbuf, gev, fused
 
 
 class _HbvRun(torch.autograd.Function):
@@ -253,11 +264,12 @@ class _HbvRun(torch.autograd.Function):
 
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
         gbuf = gev = None
-        if need_grad and dyn is not None and dyn.requires_grad and not _fused_zero_fill(spec, dyn_ncol, B):
+        gfused = False
+        if need_grad and dyn is not None and dyn.requires_grad:
+            if gplane is None:
+                gplane = start_grad_plane(spec, dyn, t_off, _checked=True)
             if gplane is not None:
-                gbuf, gev = gplane            # started earlier (start_grad_plane)
-            else:
-                gbuf, gev = start_grad_plane(spec, dyn, _checked=True)
+                gbuf, gev, gfused = gplane    # (possibly started before the warm-up kernel)
 
         flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
         state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
@@ -306,7 +318,7 @@ class _HbvRun(torch.autograd.Function):
         ctx.K = K
         ctx.has = (dyn is not None, sta is not None)
         ctx.muwts_shape = None if muwts is None else tuple(muwts.shape)
-        ctx.gbuf, ctx.gev = gbuf, gev
+        ctx.gbuf, ctx.gev, ctx.gfused = gbuf, gev, gfused
         ctx.save_for_backward(forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in)
         ctx.set_materialize_grads(False)
         outs = [flux[f] for f in range(spec.nflux)]
@@ -342,6 +354,7 @@ class _HbvRun(torch.autograd.Function):
         if dyn is not None:
             if ctx.gbuf is not None:
                 gdyn_full, ctx.gbuf = ctx.gbuf, None
+                zero_fill = 1 if ctx.gfused else 0
                 if ctx.gev is not None:
                     torch.cuda.current_stream(dev).wait_event(ctx.gev)
             elif _fused_zero_fill(spec, dyn_ncol, B):
