@@ -105,3 +105,40 @@ def test_model_attributes_match_reference_contract():
     M2 = hydrodl2.load_model('hbv_1_1p', ver_name='Hbv_1_1p')
     m2 = M2({'dynamic_params': {'Hbv_1_1p': []}, 'nmul': 16}, device=torch.device('cpu'))
     assert m2.learnable_param_count == 226 and 'capillary' in m2.flux_names
+
+
+def test_host_side_policies():
+    """Choices made on the host (no GPU needed): checkpoint interval, gradient-plane mode."""
+    from hydrodl2_b200 import _cabi as A, ops
+    import hydrodl2_b200 as hydrodl2
+    lib = A.load()
+    # every state while it fits 16 GiB (20 B per lane-step), else every 16th
+    assert lib.hbv_b200_auto_ckpt(730, 531, 16) == 1           # C2
+    assert lib.hbv_b200_auto_ckpt(730, 22500, 16) == 1         # north-star shard: 5.3 GB
+    assert lib.hbv_b200_auto_ckpt(17520, 2500, 16) == 1        # C4 per GPU: 14 GB
+    assert lib.hbv_b200_auto_ckpt(17520, 20000, 16) == 16      # C4 on one GPU: 112 GB
+    dev = torch.device('cpu')
+    hbv = hydrodl2.load_model('hbv', ver_name='Hbv')({'dynamic_params': {'Hbv': ['parBETA', 'parBETAET']}, 'nmul': 16}, device=dev)
+    p11 = hydrodl2.load_model('hbv_1_1p', ver_name='Hbv_1_1p')
+    d14 = list(p11({'dynamic_params': {'Hbv_1_1p': []}, 'nmul': 16}, device=dev).parameter_bounds)
+    m14 = p11({'dynamic_params': {'Hbv_1_1p': d14}, 'nmul': 16}, device=dev)
+    prev, ops.FUSED_ZERO_FILL = ops.FUSED_ZERO_FILL, None
+    try:
+        s2 = hbv._spec(hbv.dynamic_params, True)
+        assert ops._fused_zero_fill(s2, 210, 531) is False      # small grid: memset in stream order
+        assert ops._fused_zero_fill(s2, 210, 22500) is True     # large grid: the adjoint writes its rows
+        s14 = m14._spec(m14.dynamic_params, True)
+        assert ops._fused_zero_fill(s14, 226, 531) is True      # dense-dynamic: always
+        hbv4 = hydrodl2.load_model('hbv', ver_name='Hbv')({'dynamic_params': {'Hbv': ['parBETA']}, 'nmul': 4}, device=dev)
+        assert ops._fused_zero_fill(hbv4._spec(hbv4.dynamic_params, True), 50, 100000) is False
+    finally:
+        ops.FUSED_ZERO_FILL = prev
+
+
+def test_cpu_tensors_are_rejected():
+    """There is no CPU path: a forward on CPU tensors fails loudly instead of falling back."""
+    import hydrodl2_b200 as hydrodl2
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'dynamic_params': {'Hbv': []}, 'nmul': 4}, device=torch.device('cpu'))
+    with pytest.raises(RuntimeError, match='no CPU path|CUDA'):
+        m({'x_phy': torch.zeros(5, 3, 3)}, torch.zeros(5, 3, 12 * 4 + 2))
