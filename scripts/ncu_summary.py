@@ -94,6 +94,8 @@ def full(src, dst, workload=None):
                 targs = [a.strip() for a in name.split('<')[1].split('>')[0].split(',')] if '<' in name else []
                 if base == 'hbv_fwd_kernel' and len(targs) >= 3 and targs[2] == '0':
                     base = 'hbv_fwd_warmup'
+                if base == 'hbv_fwd_lean_kernel' and len(targs) >= 9 and targs[8] == '0':
+                    base = 'hbv_fwd_warmup'
                 traffic.setdefault(base, t)
                 f.write(f'| **DRAM traffic per launch** | {t / 1e9:.3f} GB |\n')
             except Exception:
@@ -102,8 +104,10 @@ def full(src, dst, workload=None):
     if workload:
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         cur = json.load(open(tp)) if os.path.exists(tp) else {}
-        short = {'hbv_fwd_kernel': 'hbv_fwd', 'hbv_bwd_kernel': 'hbv_bwd'}
-        cur.setdefault(workload, {})
+        short = {'hbv_fwd_kernel': 'hbv_fwd', 'hbv_bwd_kernel': 'hbv_bwd',
+                 'hbv_fwd_lean_kernel': 'hbv_fwd', 'hbv_bwd_lean_kernel': 'hbv_bwd',
+                 'hbv_fwd_dense_kernel': 'hbv_fwd', 'hbv_bwd_dense_kernel': 'hbv_bwd'}
+        cur[workload] = {}        # one capture = one consistent set of kernels
         for k, v in traffic.items():
             cur[workload][short.get(k, k)] = v
         json.dump(cur, open(tp, 'w'), indent=1, sort_keys=True)
