@@ -25,6 +25,44 @@ def shard_bounds(n_basins: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_gages(outlet_topo: torch.Tensor, world: int) -> list[tuple[torch.Tensor, torch.Tensor]]:
+    """Partition the pair routing of `Hbv_2_hourly` (hbv_2_hourly.py:800-850) so that it needs no
+    exchange: `outlet_topo[g, u] != 0` says unit u drains to gage g, and a unit may drain to
+    several (nested) gages, so the atoms that can be placed independently are the connected
+    components of that bipartite graph.  Components are assigned to ranks largest first, each to
+    the rank with the fewest units so far.  Returns, per rank, (gage indices, unit indices), both
+    sorted; rank r then runs the model on `x[:, units_r]`, `outlet_topo[gages_r][:, units_r]`."""
+    if world <= 0:
+        raise ValueError(f'bad world size {world}')
+    topo = (outlet_topo != 0).cpu()
+    n_g, n_u = topo.shape
+    parent = list(range(n_g + n_u))          # union-find over gages [0, n_g) and units [n_g, n_g + n_u)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for g, u in topo.nonzero().tolist():
+        ra, rb = find(g), find(n_g + u)
+        if ra != rb:
+            parent[rb] = ra
+    comps: dict[int, tuple[list, list]] = {}
+    for g in range(n_g):
+        comps.setdefault(find(g), ([], []))[0].append(g)
+    for u in range(n_u):
+        comps.setdefault(find(n_g + u), ([], []))[1].append(u)
+    order = sorted(comps.values(), key=lambda c: (-len(c[1]), c[0][:1], c[1][:1]))
+    out = [([], []) for _ in range(world)]
+    for gs, us in order:
+        r = min(range(world), key=lambda k: (len(out[k][1]), k))
+        out[r][0].extend(gs)
+        out[r][1].extend(us)
+    return [(torch.tensor(sorted(g), dtype=torch.long), torch.tensor(sorted(u), dtype=torch.long))
+            for g, u in out]
+
+
 def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     """(rank, local_rank, world) from torchrun's environment; initialises the process group
     when WORLD_SIZE > 1."""

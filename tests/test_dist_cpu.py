@@ -80,3 +80,28 @@ def test_two_rank_sharding_matches_single_process():
         assert torch.allclose(pt['g'], g_ref, rtol=1e-5, atol=1e-7)
         assert pt['slow'] == float(world)
     assert parts[0]['lo'] == 0 and parts[-1]['hi'] == B
+
+
+def test_shard_gages_keeps_nested_gages_together():
+    """Units that drain to several (nested) gages stay on the rank of all of those gages; every
+    gage and unit is placed exactly once; the unit counts are balanced."""
+    import torch
+    from hydrodl2_b200.dist import shard_gages
+    g = torch.Generator().manual_seed(3)
+    n_g, n_u = 12, 96
+    topo = torch.zeros(n_g, n_u)
+    for k in range(6):                       # six independent river systems of 16 units ...
+        topo[2 * k, 16 * k:16 * k + 16] = 1  # ... each with an outlet gage
+        topo[2 * k + 1, 16 * k:16 * k + int(torch.randint(4, 12, (1,), generator=g))] = 1  # and a nested one
+    parts = shard_gages(topo, 4)
+    all_g = torch.cat([p[0] for p in parts])
+    all_u = torch.cat([p[1] for p in parts])
+    assert sorted(all_g.tolist()) == list(range(n_g)) and sorted(all_u.tolist()) == list(range(n_u))
+    for gs, us in parts:
+        sub = topo[gs]
+        inside = torch.zeros(n_u, dtype=torch.bool)
+        inside[us] = True
+        assert not sub[:, ~inside].any()     # no gage of this rank needs a unit of another rank
+        assert (topo[:, us].sum(0) == sub[:, us].sum(0)).all()   # and none of its units feeds a foreign gage
+    sizes = sorted(len(p[1]) for p in parts)
+    assert sizes == [16, 16, 32, 32]
