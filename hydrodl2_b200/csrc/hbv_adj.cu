@@ -127,6 +127,13 @@ __device__ __forceinline__ void adj_eval(const float (&y)[5], const float (&p)[A
     E.dEt = E.we + (1.f - E.we) * Ep * E.be * bexp * E.ef1 * inv_SM;
 }
 
+// 1/d to ~0.5 ulp without the IEEE-division slow path (MUFU.RCP + one Newton-Raphson step); the
+// Jacobian diagonals are >= 1/dt > 0 and the 2x2 determinant is >= 1/dt^2
+__device__ __forceinline__ float rcp_nr(float d) {
+    float r = rcp_approx(d);
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+
 // J = I/dt - d f/d y, block lower triangular (rows: SP, MW | SM | SUZ | SLZ).
 struct AdjJac { float j00, j01, j10, j11, j20, j21, j22, j30, j31, j32, j33, j43, j44; };
 
@@ -167,12 +174,12 @@ __device__ __forceinline__ int adj_newton(float (&x)[5], const float (&p)[ADJ_NP
         for (int s = 0; s < 5; ++s) { G[s] = (x[s] - xt[s]) * inv_dt - E.f[s]; res = fmaxf(res, fabsf(G[s])); }
         AdjJac J;
         adj_jac(E, p, inv_dt, J);
-        const float idet = 1.0f / (J.j00 * J.j11 - J.j01 * J.j10);
+        const float idet = rcp_nr(J.j00 * J.j11 - J.j01 * J.j10);
         const float d0 = (G[0] * J.j11 - J.j01 * G[1]) * idet;
         const float d1 = (J.j00 * G[1] - J.j10 * G[0]) * idet;
-        const float d2 = (G[2] - J.j20 * d0 - J.j21 * d1) / J.j22;
-        const float d3 = (G[3] - J.j30 * d0 - J.j31 * d1 - J.j32 * d2) / J.j33;
-        const float d4 = (G[4] - J.j43 * d3) / J.j44;
+        const float d2 = (G[2] - J.j20 * d0 - J.j21 * d1) * rcp_nr(J.j22);
+        const float d3 = (G[3] - J.j30 * d0 - J.j31 * d1 - J.j32 * d2) * rcp_nr(J.j33);
+        const float d4 = (G[4] - J.j43 * d3) * rcp_nr(J.j44);
         x[0] -= d0; x[1] -= d1; x[2] -= d2; x[3] -= d3; x[4] -= d4;
         ++n;
         if (res <= tol) { conv = true; break; }
@@ -214,6 +221,10 @@ hbv_adj_fwd_kernel(const KDesc d, const AdjFwdPtrs io, const float tol, const in
     load_step<NPAR, DM>(d, fptr, f_tstride, dyn_lane, dyn_tstride, dynmask, 0, nxt);
     for (int t0 = 0; t0 < d.T; t0 += ADJ_TC) {
         const int tcn = min(ADJ_TC, d.T - t0);
+        // not unrolled: the Newton body is ~700 SASS instructions; ptxas unrolled this loop x4 and
+        // the 44 KB loop body ran out of the instruction cache (ncu: 2.9 `no_instruction` stall
+        // cycles per issued instruction, the largest stall reason of the kernel)
+#pragma unroll 1
         for (int tc = 0; tc < tcn; ++tc) {
             const int t = t0 + tc;
             const StepIn<DS::NS> cur = nxt;
@@ -313,12 +324,12 @@ hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
         gx[3] += gQ * E.m3 * (p[HBV_P_K0] * E.u + p[HBV_P_K1]);
         gx[4] += gQ * E.m4 * p[HBV_P_K2];
         // J^T lambda = gx (upper block triangular)
-        const float l4 = gx[4] / J.j44;
-        const float l3 = (gx[3] - J.j43 * l4) / J.j33;
-        const float l2 = (gx[2] - J.j32 * l3) / J.j22;
+        const float l4 = gx[4] * rcp_nr(J.j44);
+        const float l3 = (gx[3] - J.j43 * l4) * rcp_nr(J.j33);
+        const float l2 = (gx[2] - J.j32 * l3) * rcp_nr(J.j22);
         const float r0 = gx[0] - J.j20 * l2 - J.j30 * l3;
         const float r1 = gx[1] - J.j21 * l2 - J.j31 * l3;
-        const float idet = 1.0f / (J.j00 * J.j11 - J.j01 * J.j10);
+        const float idet = rcp_nr(J.j00 * J.j11 - J.j01 * J.j10);
         const float l0 = (r0 * J.j11 - J.j10 * r1) * idet;
         const float l1 = (J.j00 * r1 - J.j01 * r0) * idet;
         // dL/dp = lambda^T df/dp + gQ dQ/dp, flux by flux
