@@ -327,7 +327,7 @@ def run_b200(args):
     def k_eff(wl, B):      # the checkpoint interval the run actually uses (0 = library default)
         return args.ckpt or int(_cabi.load().hbv_b200_auto_ckpt(wl['T'], B, NMUL))
 
-    def train_step(model, x_dev, p_dev):
+    def train_step(model, x_dev, p_dev, allreduce=True):
         p_dev.grad = None
         out = model({'x_phy': x_dev}, p_dev)
         loss = out['streamflow'].sum()
@@ -335,7 +335,7 @@ def run_b200(args):
         # gradient of a bias on the static-parameter row shared by all basins (stands in for
         # the shared NN weights): the one quantity that needs a cross-GPU reduction
         gshared = p_dev.grad[-1].sum(dim=0)
-        if not NO_ALLREDUCE:
+        if allreduce and not NO_ALLREDUCE:
             D.allreduce_shared_grad(gshared)
         return out, loss, gshared
 
@@ -414,14 +414,26 @@ def run_b200(args):
     # the timed step: eager by default; --graph replays the same step from a CUDA graph
     graph_note = 'eager'
     step_fn = lambda: train_step(model, x_dev, p_dev)   # noqa: E731
-    if args.graph and world == 1:
+    if args.graph:
         try:
             from hydrodl2_b200.graphs import GraphedStep
-            gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev), warmup=3, device=dev)
-            step_fn = gstep.replay
-            graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+            # the collective stays outside the graph (capturing NCCL hung on 2 GPUs): each rank
+            # replays its own step, then the shared-gradient all-reduce runs eagerly on the
+            # graph's static output
+            gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
+            if world == 1:
+                step_fn = gstep.replay
+                graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+            else:
+                def step_fn():
+                    _, _, gsh = gstep.replay()
+                    if not NO_ALLREDUCE:
+                        D.allreduce_shared_grad(gsh)
+                graph_note = ('cuda graph replay of the step (hydrodl2_b200.graphs.GraphedStep) + eager NCCL '
+                              'all-reduce of the shared gradient')
         except Exception as exc:   # pragma: no cover - depends on driver / NCCL
             graph_note = f'eager (graph capture failed: {type(exc).__name__}: {exc})'
+            step_fn = lambda: train_step(model, x_dev, p_dev)   # noqa: E731
             torch.cuda.synchronize(dev)
     ms_step = timed(step_fn, args.steps, args.warmup, sampler) / args.steps
     value = world * B * T_MAIN / (ms_step * 1e-3)
@@ -584,7 +596,8 @@ def main():
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='time the eager step instead of a CUDA-graph replay of it (single GPU: the step '
                          'is ~0.55 ms of kernels, about what one eager Python step costs the host, so the '
-                         'eager number depends on the host CPU; multi-GPU runs are always eager)')
+                         'eager number depends on the host CPU; with several GPUs the all-reduce runs '
+                         'eagerly after each replay)')
     ap.set_defaults(graph=True)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

@@ -12,8 +12,9 @@ gradient memset, and an NCCL all-reduce if there is one) can be captured once an
 
 Measured on B200 (531 basins, 0.55 ms of kernels per training step): replay 0.55 ms; the eager
 step 0.57-0.71 ms depending on the box's host CPU (one eager step costs the host about as much as
-the kernels take).  `bench.py` times the replay on one GPU and the eager step on several (capturing
-a step that contains an NCCL collective hung on 2 GPUs).
+the kernels take).  `bench.py` times the replay; with several GPUs the NCCL all-reduce of the
+shared gradient stays outside the graph and runs eagerly on the graph's static output after each
+replay (capturing a step that contains the collective hung on 2 GPUs): 0.565 ms per step on 2 GPUs.
 
 Inputs must live in static tensors (copy new data into them before `replay()`); the dynamic-
 parameter dropout draw (`dy_drop > 0`, a CPU RNG draw per forward, hbv.py:240-246) would be
