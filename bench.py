@@ -315,6 +315,7 @@ def run_b200(args):
         print(f'bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    numa = '' if os.environ.get('HBV_BENCH_NO_NUMA') == '1' else D.bind_to_gpu_numa_node(local)
     _cabi.load()
     peak, peak_src = measured_peak_gbs()
 
@@ -502,7 +503,7 @@ def run_b200(args):
                 'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
                 'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': k_eff(wl, B),
                 'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
-                'launch': graph_note, 'eager_ms_per_step': ms_eager,
+                'launch': graph_note, 'eager_ms_per_step': ms_eager, 'host_affinity': numa or 'unchanged',
                 'l2': 'inputs larger than L2: parameters + gradient = '
                       f'{2 * (wl["warm_up"] + T_MAIN) * B * ncol * 4 / 1e6:.0f} MB per step vs 126 MB L2',
             },

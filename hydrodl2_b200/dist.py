@@ -78,6 +78,35 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(device_index: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (from sysfs), so pinned
+    host buffers are first-touched in memory local to that GPU's PCIe root — matters for the
+    host <-> device legs when several ranks share a two-socket host.  Best effort: returns a
+    short description of what was done ('' when the topology cannot be read)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[device_index]) if vis else device_index
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(':')[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = f'/sys/bus/pci/devices/{bus}'
+        node = int(open(f'{base}/numa_node').read())
+        cpus = set()
+        for part in open(f'{base}/local_cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return ''
+        os.sched_setaffinity(0, cpus)
+        return f'numa node {node}, {len(cpus)} cpus'
+    except Exception:
+        return ''
+
+
 def allreduce_shared_grad(g: torch.Tensor) -> torch.Tensor:
     """Sum a shared-parameter gradient over ranks (in place); no-op for a single process."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -198,3 +198,24 @@ def test_lean_fused_zero_fill_on_poisoned_memory(monkeypatch):
     assert torch.isfinite(grads[True]).all()
     assert_close(grads[True], grads[False], 1e-7, 'fused zero fill vs memset')
     assert (grads[True][:warm] == 0).all()
+
+
+@pytest.mark.parametrize('T,B,warm', [(1, 1, 0), (2, 3, 0), (3, 1, 1), (5, 2, 2), (13, 7, 0), (17, 33, 4)])
+def test_lean_tiny_shapes(T, B, warm, monkeypatch):
+    """Edge sizes of the small-grid (cp.async ring) forms: fewer steps than the ring is deep, a single
+    basin, a partial warp, a one-step warm-up."""
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    x = O.synthetic_forcing(T, B, seed=81)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(82))
+    pc = p.clone().requires_grad_(True)
+    ref, ref_states = O.forward_packed('hbv', x, pc, nmul=NMUL, warm_up=warm, dynamic_params=D2)
+    ref['streamflow'].sum().backward()
+    n0 = _lean_count()
+    out, grad, m = _run_packed('hbv', 'Hbv', 13, x, p, dev, True, monkeypatch, warm)
+    assert _lean_count() - n0 == (3 if warm else 2)      # (warm-up K1s +) K1s + K2s
+    for k, v in ref.items():
+        assert_close(out[k], v, RTOL_FLUX, f'tiny T={T} B={B}:{k}')
+    assert_close(grad, pc.grad, RTOL_GRAD, f'tiny T={T} B={B}:grad')
+    for name, s, r in zip(m.state_names, m.get_states(), ref_states):
+        assert_close(s, r, RTOL_FLUX, f'tiny T={T} B={B}:state {name}')
