@@ -105,3 +105,36 @@ def test_shard_gages_keeps_nested_gages_together():
         assert (topo[:, us].sum(0) == sub[:, us].sum(0)).all()   # and none of its units feeds a foreign gage
     sizes = sorted(len(p[1]) for p in parts)
     assert sizes == [16, 16, 32, 32]
+
+
+def _allreduce_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from hydrodl2_b200.dpl import allreduce_gradients
+    lin = torch.nn.Linear(3, 2)
+    lin.weight.grad = torch.full((2, 3), float(rank + 1))
+    lin.bias.grad = torch.arange(2, dtype=torch.float32) * (rank + 1)
+    n = allreduce_gradients(lin.parameters(), average=True)
+    q.put((rank, n, lin.weight.grad.clone(), lin.bias.grad.clone()))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2():
+    """dpl.allreduce_gradients: one flat collective, averaged, written back in place."""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, 29541, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, n, w, b in res:
+        assert n == 8
+        assert torch.allclose(w, torch.full((2, 3), 1.5))
+        assert torch.allclose(b, torch.tensor([0.0, 1.5]))
