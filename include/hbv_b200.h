@@ -163,7 +163,13 @@ typedef struct hbv_bwd_io {
                         the component weights, dL/dQsim[t,b] * Qsim_lane[t,b,j]                 */
 } hbv_bwd_io_t;
 
-/* K1: fused forward recurrence + nmul aggregation (hbv.py:363-511). */
+/* K1: fused forward recurrence + nmul aggregation (hbv.py:363-511).
+ * K1 / K2 each exist in three interchangeable compilations, chosen from the descriptor alone (same
+ * arithmetic, results equal to fp32 round-off): the general kernels (any dynamic set, dropout,
+ * muwts, state series, any nmul), the standard-layout kernels (nvar 3 in prcp/tmean/pet order,
+ * nmul 16, columns 16*i, the shipped dynamic sets; adjoint: ckpt_interval 1 and an upstream
+ * gradient on the streamflow series only) and the TMA-staged kernels (>= 8 time-varying
+ * parameters filling at least half of a row, full-GPU grids).  See DESIGN.md section 4. */
 HBV_API int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream);
 
 /* K2: checkpointed adjoint of K1. */
