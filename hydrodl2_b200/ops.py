@@ -258,9 +258,20 @@ class _HbvRun(torch.autograd.Function):
         K = spec.ckpt_interval or int(lib.hbv_b200_auto_ckpt(T, B, nmul))   # 0 = auto
         d.ckpt_interval = K
         nseg = (T + K - 1) // K
-        ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
-        if not need_grad:
-            d.ckpt_interval = 0
+        # `hbv_2` family: the per-step state series (hbv_2.py:571-575, the state AFTER every step)
+        # and the every-state store of the adjoint (the state BEFORE every step) are the same
+        # numbers shifted by one step — with K = 1 one [T + 1, 5, B, nmul] buffer serves both (the
+        # kernel writes planes 0 .. T-1, the final state becomes plane T): no second 20 B per
+        # lane-step stream, and the run stays eligible for the standard-layout kernels.
+        alias_series = bool(spec.state_series) and K == 1
+        ck_full = None
+        if alias_series:
+            ck_full = torch.empty((T + 1, 5, B, nmul), device=dev, dtype=torch.float32)
+            ckpt = ck_full[:T]
+        else:
+            ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
+            if not need_grad:
+                d.ckpt_interval = 0
 
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
         gbuf = gev = None
@@ -274,7 +285,7 @@ class _HbvRun(torch.autograd.Function):
         flux = torch.empty((A.HBV_MAX_FLUX, T, B), device=dev, dtype=torch.float32)
         state_out = torch.empty((5, B, nmul), device=dev, dtype=torch.float32)
         series = (torch.empty((5, T, B, nmul), device=dev, dtype=torch.float32)
-                  if spec.state_series else None)
+                  if (spec.state_series and not alias_series) else None)
         io = A.HbvFwdIO()
         io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn_run), _ptr(sta)
         io.drop, io.attrs, io.muwts = _ptr(drop), _ptr(attrs), _ptr(mu)
@@ -286,6 +297,11 @@ class _HbvRun(torch.autograd.Function):
         with torch.cuda.device(dev):
             with _timed('hbv_fwd', dev):
                 A.check(lib.hbv_b200_fwd(C.byref(d), C.byref(io), stream), 'fwd')
+            if alias_series:
+                ck_full[T].copy_(state_out)
+                series = ck_full[1:].permute(1, 0, 2, 3)          # [5, T, B, nmul] view
+                if not need_grad:
+                    ckpt = None
 
             routed = uh = bfi = bfi_ws = None
             rdesc = route_t = None

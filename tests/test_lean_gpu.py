@@ -4,7 +4,7 @@ They serve the throughput regime (large grids), so the cases use > 2,368 basins 
   * `hbv` / `hbv_1_1p` with the shipped dynamic set against the CPU oracle on the same seeded
     inputs (1e-5 fluxes / states, 1e-4 gradients), with warm-up, partial last CTA, odd B;
   * every variant against K1 / K2 on the same inputs (HBV_B200_LEAN=0): same step arithmetic,
-    agreement to fp32 contraction noise (1e-6);
+    agreement to fp32 contraction noise (5e-6);
 and check through the library's dispatch counter that the lean kernels are the ones that ran.
 """
 
@@ -16,6 +16,9 @@ from conftest import RTOL_FLUX, RTOL_GRAD, assert_close
 pytestmark = pytest.mark.gpu
 
 NMUL = 16
+# two compilations of the same step arithmetic differ by FMA-contraction choices; the largest
+# relative difference sits on the excess flux (a cancellation, SM1 - FC): 2e-6 measured
+XTOL = 5e-6
 D2 = ['parBETA', 'parBETAET']
 D3 = ['parBETA', 'parK0', 'parBETAET']
 
@@ -62,8 +65,8 @@ def test_lean_packed_vs_oracle(model, cls, npar, B, monkeypatch):
     out0, grad0, _ = _run_packed(model, cls, npar, x, p, dev, False, monkeypatch, warm)
     assert _lean_count() - n0 == 0
     for k in ref:
-        assert_close(out[k], out0[k], 1e-6, f'lean vs K1 {model} B={B}:{k}')
-    assert_close(grad, grad0, 1e-6, f'lean vs K2 {model} B={B}:grad')
+        assert_close(out[k], out0[k], XTOL, f'lean vs K1 {model} B={B}:{k}')
+    assert_close(grad, grad0, XTOL, f'lean vs K2 {model} B={B}:grad')
 
 
 def test_lean_forward_only_no_grad(monkeypatch):
@@ -141,9 +144,9 @@ def test_lean_hbv_2_matches_k1_k2(B, monkeypatch):
     out0, g0, n0 = run(False)
     assert (n1, n0) == (2, 0)
     for k in out0:
-        assert_close(out1[k], out0[k], 1e-6, f'hbv_2 lean vs K1 B={B}:{k}')
+        assert_close(out1[k], out0[k], XTOL, f'hbv_2 lean vs K1 B={B}:{k}')
     for a, b, n in zip(g1, g0, ('dyn', 'static')):
-        assert_close(a, b, 1e-6, f'hbv_2 lean vs K2 B={B}:grad {n}')
+        assert_close(a, b, XTOL, f'hbv_2 lean vs K2 B={B}:grad {n}')
 
 
 def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
@@ -166,9 +169,9 @@ def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
     out1, g1, n1 = run(True)
     out0, g0, n0 = run(False)
     assert (n1, n0) == (2, 0)
-    assert_close(out1['Qs'], out0['Qs'], 1e-6, 'hourly lean vs K1: Qs')
+    assert_close(out1['Qs'], out0['Qs'], XTOL, 'hourly lean vs K1: Qs')
     for a, b, n in zip(g1, g0, ('dyn', 'static')):
-        assert_close(a, b, 1e-6, f'hourly lean vs K2: grad {n}')
+        assert_close(a, b, XTOL, f'hourly lean vs K2: grad {n}')
 
 
 def test_lean_fused_zero_fill_on_poisoned_memory(monkeypatch):

@@ -146,11 +146,12 @@ def _run_split(g, dev, ckpt=16, state_series=True):
     return m, out, params
 
 
+@pytest.mark.parametrize('ckpt', [16, 0])     # 0 = auto (K = 1): the state series aliases the stored states
 @pytest.mark.parametrize('case', SPLIT)
-def test_split_forward_matches_reference(case):
+def test_split_forward_matches_reference(case, ckpt):
     dev = torch.device('cuda:0')
     g = load_golden(case)
-    m, out, _ = _run_split(g, dev)
+    m, out, _ = _run_split(g, dev, ckpt)
     assert set(out.keys()) == set(g['out'].keys())
     for k, ref in g['out'].items():
         assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k}')
@@ -158,12 +159,12 @@ def test_split_forward_matches_reference(case):
         assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name}')
 
 
-@pytest.mark.parametrize('ckpt', [1, 16])
+@pytest.mark.parametrize('ckpt,series', [(1, False), (16, True), (0, True), (1, True)])
 @pytest.mark.parametrize('case', SPLIT)
-def test_split_gradient_matches_reference(case, ckpt):
+def test_split_gradient_matches_reference(case, ckpt, series):
     dev = torch.device('cuda:0')
     g = load_golden(case)
-    m, out, params = _run_split(g, dev, ckpt, state_series=(ckpt == 16))
+    m, out, params = _run_split(g, dev, ckpt, state_series=series)
     loss = 0.0
     for k, c in g['cot'].items():
         loss = loss + (out[k] * c.to(dev)).sum()
@@ -172,6 +173,9 @@ def test_split_gradient_matches_reference(case, ckpt):
     assert_close(params[1].grad, g['grad']['p1'], RTOL_GRAD, f'{case}:grad static K={ckpt}')
     if len(params) > 2:
         assert_close(params[2].grad, g['grad']['p2'], RTOL_GRAD, f'{case}:grad distr K={ckpt}')
+    if series:
+        for name, s in zip(m.state_names, m._state_cache):
+            assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name} K={ckpt}')
 
 
 def test_mts_matches_reference():
