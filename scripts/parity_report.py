@@ -42,6 +42,44 @@ def main():
         worst['grad'] = max(worst['grad'], eg)
         print(f'{case:22s} flux {ef:.2e} ({kf})  state {es:.2e}  grad {eg:.2e}')
     print('worst', {k: f'{v:.2e}' for k, v in worst.items()}, ' tolerances: flux/state 1e-5, grad 1e-4')
+    full_size(dev)
+
+
+def full_size(dev):
+    """Margins against the CPU oracle at BASELINE sizes: C2 in full (K1s / K2s ring forms) and a
+    48-basin slice of the 22,500-basin shards (K1s / K2s large-grid forms, K1d / K2d)."""
+    import hydrodl2_b200 as hydrodl2
+    from oracle import hbv_oracle as O
+    D2 = ['parBETA', 'parBETAET']
+    D14 = ['parBETA', 'parFC', 'parK0', 'parK1', 'parK2', 'parLP', 'parPERC', 'parUZL', 'parTT',
+           'parCFMAX', 'parCFR', 'parCWH', 'parBETAET', 'parC']
+
+    def run(name, cls, npar, dyn, T, B, warm, lo, nb, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = O.synthetic_forcing(T, B, seed=seed).to(dev) if B <= 4096 else None
+        if x is None:
+            import test_fullsize_gpu as F
+            x, p = F._device_inputs(T, B, npar * 16 + 2, dev, seed)
+        else:
+            p = torch.randn(T, B, npar * 16 + 2, generator=g, device=dev)
+        M = hydrodl2.load_model(name, ver_name=cls)
+        m = M({'warm_up': warm, 'dynamic_params': {cls: dyn}, 'nmul': 16}, device=dev)
+        pg = p.clone().requires_grad_(True)
+        out = m({'x_phy': x}, pg)
+        out['streamflow'].sum().backward()
+        xs, ps = x[:, lo:lo + nb].cpu(), p[:, lo:lo + nb].cpu()
+        pc = ps.clone().requires_grad_(True)
+        ref, ref_states = O.forward_packed(name, xs, pc, nmul=16, warm_up=warm, dynamic_params=dyn)
+        ref['streamflow'].sum().backward()
+        ef = max(maxnorm_err(out[k][lo:lo + nb] if k == 'BFI' else out[k][:, lo:lo + nb], v) for k, v in ref.items())
+        es = max(maxnorm_err(s[lo:lo + nb], r) for s, r in zip(m.get_states(), ref_states))
+        eg = maxnorm_err(pg.grad[:, lo:lo + nb], pc.grad)
+        print(f'{name:9s} {B:6d} x {T:4d} (warm-up {warm:3d}) vs oracle on basins [{lo}, {lo + nb}): '
+              f'flux {ef:.2e}  state {es:.2e}  grad {eg:.2e}')
+
+    run('hbv', 'Hbv', 13, D2, 1095, 531, 365, 0, 531, 20261017)
+    run('hbv', 'Hbv', 13, D2, 730, 22500, 0, 11111, 48, 5)
+    run('hbv_1_1p', 'Hbv_1_1p', 14, D14, 730, 22500, 0, 11111, 48, 5)
 
 
 if __name__ == '__main__':
