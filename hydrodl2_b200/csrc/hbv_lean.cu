@@ -299,41 +299,84 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         pf -= sf; pd -= sd; pq -= d.B;
     };
 
+    // ---- ring form (RD > 0, one-warp CTA): the warp's inputs of a step are staged by FOUR cp.async
+    // instructions instead of one per value and lane (LDGSTS costs the LSU ~8 cycles per warp
+    // instruction whatever its width; ncu showed the 11-instruction form LSU-limited on large grids):
+    //   A  4 B x 8 lanes   P, T, PET and dL/dQ of the two basins         -> slot[0 .. 7]
+    //   B  8 B x 16*ND     the 64 B run of every dynamic parameter        -> slot[8 + 32 k + lane]
+    //   C 16 B x 32 lanes  stored states 0..3 (128 B per state and warp)  -> slot[ST + 32 s + lane]
+    //   D 16 B x 8 lanes   stored state 4
+    // and read back by every lane with one LDS.128 (P, T, PET, dL/dQ) + ND + 5 LDS.  A lane now reads
+    // what other lanes copied: cp.async.wait_group is followed by __syncwarp().
     extern __shared__ __align__(16) float ringmem[];
-    constexpr int NSP = (4 + ND + 5) | 1;
+    constexpr int NDR = DS::NDYN;
+    constexpr int PARB = 8, STB = 8 + 32 * NDR, SLOT = 8 + 32 * (NDR + 5);
+    constexpr int NB = (16 * NDR + 31) / 32;
     constexpr int RDS = RD > 0 ? RD : 2;
-    float* const ring0 = ringmem + tid * NSP;
-    constexpr int step_floats = LBPB * LNM * NSP;
-    float* const ring_end = ring0 + RDS * step_floats;
-    float* wp = ring0;
-    const float* rp = ring0;
+    float* const ring_end = ringmem + RDS * SLOT;
+    float* wp = ringmem;
+    const float* rp = ringmem;
+    const int b0w = blockIdx.x * LBPB;
+    const int nbw = min(LBPB, d.B - b0w);
+    const int kA = tid & 15, bbA = tid >> 4;
+    const bool actA = kA < 4;
+    const int64_t rowA = (int64_t)(d.T - 1) * d.B + min(b0w + bbA, d.B - 1);
+    const float* srcA = (kA < 3) ? io.forcing + rowA * 3 + kA : io.gflux[HBV_F_QSIM] + rowA;
+    const int64_t strA = (kA < 3) ? sf : (int64_t)d.B;
+    const int dstA = 4 * bbA + kA;
+    const float* srcB[NB];
+    int dstB[NB];
+    bool actB[NB];
+#pragma unroll
+    for (int o = 0; o < NB; ++o) {
+        const int gq = o * 32 + tid;
+        actB[o] = gq < 16 * NDR;
+        const int r = actB[o] ? (gq >> 3) : 0, q = gq & 7;
+        const int bb = r / (NDR > 0 ? NDR : 1), k = r - bb * NDR;
+        int col = 0;
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (DS::is_dyn(i, 0) && DS::slot(i) == k) col = lean_col<NPAR, DM, LAYOUT>(i);
+        srcB[o] = io.dyn + ((int64_t)(d.T - 1) * d.B + min(b0w + bb, d.B - 1)) * d.dyn_ncol + col + 2 * q;
+        dstB[o] = PARB + k * 32 + bb * 16 + 2 * q;
+    }
+    const int sC = tid >> 3, qC = tid & 7;
+    const bool actC = 4 * qC < 16 * nbw;
+    const float* srcC = io.ckpt + ((int64_t)(d.T - 1) * 5 + sC) * nlane + (int64_t)b0w * LNM + 4 * qC;
+    const float* srcD = io.ckpt + ((int64_t)(d.T - 1) * 5 + 4) * nlane + (int64_t)b0w * LNM + 4 * qC;
+    const bool actD = actC && tid < 8;
+    const int dstC = STB + sC * 32 + 4 * qC, dstD = STB + 4 * 32 + 4 * qC;
+    const int64_t strC = 5 * nlane;
     int t_stage = d.T - 1;
     auto issue = [&]() {             // stage the inputs of the next step of the sweep (if any)
         if (t_stage >= 0) {
-            cp_async4(wp + 0, pf); cp_async4(wp + 1, pf + 1); cp_async4(wp + 2, pf + 2);
-            cp_async4(wp + 3, pq);
+            if (actA) cp_async4(wp + dstA, srcA);
 #pragma unroll
-            for (int i = 0; i < NPAR; ++i)
-                if (DS::is_dyn(i, 0)) cp_async4(wp + 4 + DS::slot(i), pd + lean_col<NPAR, DM, LAYOUT>(i));
+            for (int o = 0; o < NB; ++o)
+                if (actB[o]) cp_async8(wp + dstB[o], srcB[o]);
+            if (actC) cp_async16(wp + dstC, srcC);
+            if (actD) cp_async16(wp + dstD, srcD);
+            srcA -= strA; srcC -= strC; srcD -= strC;
 #pragma unroll
-            for (int s = 4; s >= 0; --s) { pc -= nlane; cp_async4(wp + 4 + ND + s, pc); }
-            pf -= sf; pd -= sd; pq -= d.B;
+            for (int o = 0; o < NB; ++o) srcB[o] -= sd;
         }
         --t_stage;
         cp_async_commit();
-        wp += step_floats;
-        if (wp == ring_end) wp = ring0;
+        wp += SLOT;
+        if (wp == ring_end) wp = ringmem;
     };
     auto pop = [&](In& in) {
         cp_async_wait<RDS - 2>();
-        issue();
-        in.P = rp[0]; in.T = rp[1]; in.E = rp[2]; in.q = rp[3];
+        __syncwarp();                // every lane's copies of the oldest step have landed, and every
+        issue();                     // lane is done reading the slot that is refilled now
+        const float4 f = *reinterpret_cast<const float4*>(rp + 4 * bl);
+        in.P = f.x; in.T = f.y; in.E = f.z; in.q = f.w;
 #pragma unroll
-        for (int k = 0; k < ND; ++k) in.raw[k] = rp[4 + k];
+        for (int k = 0; k < NDR; ++k) in.raw[k] = rp[PARB + k * 32 + tid];
 #pragma unroll
-        for (int s2 = 0; s2 < 5; ++s2) in.S[s2] = rp[4 + ND + s2];
-        rp += step_floats;
-        if (rp == ring_end) rp = ring0;
+        for (int s2 = 0; s2 < 5; ++s2) in.S[s2] = rp[STB + s2 * 32 + tid];
+        rp += SLOT;
+        if (rp == ring_end) rp = ringmem;
     };
 
     Tape tp;
@@ -475,9 +518,8 @@ static bool lean_small_grid(const KDesc& d) {
     return (long long)d.B * LNM <= thr;
 }
 static bool lean_bwd_ring(const KDesc& d) {
-    (void)d;
     const char* e = std::getenv("HBV_B200_LEAN_BWD_RING");
-    return !(e && e[0] == '0');
+    return !(e && e[0] == '0') && d.dyn_ncol % 2 == 0;      // (8 B copies of the parameter runs)
 }
 
 constexpr int LRD_F = 12;    // small grids: forward ring depth (steps)
@@ -531,7 +573,7 @@ template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, 
 static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
-    const size_t smem = (size_t)RD * LBPB * LNM * ((4 + ND + 5) | 1) * sizeof(float);
+    const size_t smem = (size_t)RD * (8 + 32 * (ND + 5)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
     if constexpr (LBPB == 2) {
         if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol)
@@ -550,7 +592,8 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
-    return lean_bwd_ring(d) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 1, LRD_B>(d, io, st)
+    const bool aligned = reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0 && reinterpret_cast<uintptr_t>(io.ckpt) % 16 == 0;
+    return (lean_bwd_ring(d) && aligned) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 1, LRD_B>(d, io, st)
                               : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1, 0>(d, io, st);
 }
 
@@ -580,7 +623,8 @@ int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     // column of `dyn` is a time-varying parameter (split form); otherwise the one-warp form zeroes
     // its rows itself (even row width: 8 B stores)
     if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol &&
-        !(lean_bwd_ring(d) && d.dyn_ncol % 2 == 0)) return HBV_NOT_ELIGIBLE;
+        !(lean_bwd_ring(d) && reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0 &&
+          reinterpret_cast<uintptr_t>(io.ckpt) % 16 == 0)) return HBV_NOT_ELIGIBLE;
     if (io.gflux[HBV_F_QSIM] == nullptr) return HBV_NOT_ELIGIBLE;
     for (int f = 1; f < HBV_MAX_FLUX; ++f)
         if (io.gflux[f] != nullptr) return HBV_NOT_ELIGIBLE;
