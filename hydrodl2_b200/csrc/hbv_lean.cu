@@ -157,31 +157,64 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         }
     };
 
-    // ring (RD > 0): [step][thread][NSP] after the output tile; a thread only touches its own slots
-    constexpr int NSP = (3 + DS::NDYN) | 1;
+    // ring (RD > 0, one-warp CTA) after the output tile: the warp's inputs of a step are staged by
+    // two cp.async instructions (see the adjoint below for the why):
+    //   A  4 B x 6 lanes   P, T, PET of the two basins               -> slot[4 bl + k]
+    //   B  8 B x 16*ND     the 64 B run of every dynamic parameter   -> slot[8 + 32 k + lane]
+    // read back with one LDS.128 + ND LDS; cp.async.wait_group is followed by __syncwarp() because a
+    // lane reads what other lanes copied.
+    constexpr int NDR = DS::NDYN;
+    constexpr int PARB = 8, SLOT = 8 + 32 * NDR;
+    constexpr int NB = (16 * NDR + 31) / 32;
     constexpr int RDS = RD > 0 ? RD : 2;
-    float* const ring0 = tile + (WF ? LTC * tstride_s : 0) + tid * NSP;
-    constexpr int step_floats = LBPB * LNM * NSP;
-    float* const ring_end = ring0 + RDS * step_floats;
+    float* const ring0 = tile + (WF ? LTC * tstride_s : 0);
+    float* const ring_end = ring0 + RDS * SLOT;
     float* wp = ring0;
     const float* rp = ring0;
-    auto issue = [&]() {             // stage the next time step (the last row again past the end)
-        cp_async4(wp + 0, pf); cp_async4(wp + 1, pf + 1); cp_async4(wp + 2, pf + 2);
+    const int b0w = blockIdx.x * LBPB;
+    const int kA = tid & 15, bbA = tid >> 4;
+    const bool actA = kA < 3;
+    const float* srcA = io.forcing + (int64_t)min(b0w + bbA, d.B - 1) * 3 + kA;
+    const int dstA = 4 * bbA + kA;
+    const float* srcB[NB > 0 ? NB : 1];
+    int dstB[NB > 0 ? NB : 1];
+    bool actB[NB > 0 ? NB : 1];
+#pragma unroll
+    for (int o = 0; o < NB; ++o) {
+        const int gq = o * 32 + tid;
+        actB[o] = gq < 16 * NDR;
+        const int r = actB[o] ? (gq >> 3) : 0, q = gq & 7;
+        const int bb = r / (NDR > 0 ? NDR : 1), k = r - bb * NDR;
+        int col = 0;
 #pragma unroll
         for (int i = 0; i < NPAR; ++i)
-            if (DS::is_dyn(i, 0)) cp_async4(wp + 3 + DS::slot(i), pd + lean_col<NPAR, DM, LAYOUT>(i));
+            if (DS::is_dyn(i, 0) && DS::slot(i) == k) col = lean_col<NPAR, DM, LAYOUT>(i);
+        srcB[o] = io.dyn + (int64_t)min(b0w + bb, d.B - 1) * d.dyn_ncol + col + 2 * q;
+        dstB[o] = PARB + k * 32 + bb * 16 + 2 * q;
+    }
+    auto issue = [&]() {             // stage the next time step (the last row again past the end)
+        if (actA) cp_async4(wp + dstA, srcA);
+#pragma unroll
+        for (int o = 0; o < NB; ++o)
+            if (actB[o]) cp_async8(wp + dstB[o], srcB[o]);
         cp_async_commit();
-        if (++t_issue < d.T) { pf += sf; pd += sd; }
-        wp += step_floats;
+        if (++t_issue < d.T) {
+            srcA += sf;
+#pragma unroll
+            for (int o = 0; o < NB; ++o) srcB[o] += sd;
+        }
+        wp += SLOT;
         if (wp == ring_end) wp = ring0;
     };
     auto pop = [&](In& in) {         // oldest staged step
         cp_async_wait<RDS - 2>();
+        __syncwarp();
         issue();
-        in.P = rp[0]; in.T = rp[1]; in.E = rp[2];
+        const float4 f = *reinterpret_cast<const float4*>(rp + 4 * bl);
+        in.P = f.x; in.T = f.y; in.E = f.z;
 #pragma unroll
-        for (int k = 0; k < DS::NDYN; ++k) in.raw[k] = rp[3 + k];
-        rp += step_floats;
+        for (int k = 0; k < NDR; ++k) in.raw[k] = rp[PARB + k * 32 + tid];
+        rp += SLOT;
         if (rp == ring_end) rp = ring0;
     };
 
@@ -501,19 +534,23 @@ static bool lean_common_ok(const KDesc& d) {
     return !(force && force[0] == '1');
 }
 
-// Which form runs where (measured on B200, `hbv` D2 fwd+bwd, ms per kernel):
-//   basins        531     2,500    5,000    10,000   22,500
-//   K1s ring      0.24    0.79     1.46     2.51     3.61      one-warp CTAs + cp.async ring
-//   K1s regs      0.30    0.69     1.19     2.23     2.54      128-thread CTAs + register prefetch
-//   K2s ring      0.22    0.50     1.00     1.78     3.90
-//   K2s regs      0.43    0.70     1.44     2.32     4.24
-// (a ring with 128-thread CTAs was also tried for the forward at 22,500 basins: 2.95 vs 1.43 ms)
-// -> forward: ring form up to 2 warps per scheduler (37,888 lanes), register form above;
-//    adjoint: ring form everywhere (its step is long enough that prefetch distance, not the
-//    LDGSTS + LDS instruction overhead, decides).  HBV_B200_LEAN_SMALL (lanes) and
-//    HBV_B200_LEAN_BWD_RING (0/1) override for experiments.
-static bool lean_small_grid(const KDesc& d) {
-    long long thr = 148LL * 4 * 32 * 2;
+// Which form runs where (measured on B200, `hbv` D2, ms per kernel; forward = inference / training):
+//   basins          531          2,500        5,000        22,500
+//   K1s ring        0.16 / 0.16  0.24 / 0.30  0.44 / 0.66  1.76 / 3.37   one-warp CTAs + cp.async ring
+//   K1s regs        0.26 / 0.27  0.30 / 0.37  0.38 / 0.53  1.43 / 2.65   128-thread CTAs + register prefetch
+//   warm-up ring    0.065        0.097        0.113        0.365
+//   warm-up K1      0.090        0.113        0.133        0.415
+//   K2s ring        0.21         0.50         1.00         4.34          (4 wide copies per step)
+//   K2s regs        0.43         0.70         1.44         4.24 + memset
+// -> forward: ring form up to 3 warps per scheduler (56,832 lanes; 2 when it also stores the
+//    states), register form above; the
+//    states-only warm-up run and the adjoint: ring form everywhere.  HBV_B200_LEAN_SMALL (lanes)
+//    and HBV_B200_LEAN_BWD_RING (0/1) override for experiments.
+static bool lean_small_grid(const KDesc& d, bool storing_states = false) {
+    // (with the state stores of a training run the register form already wins at 2.1 warps per
+    // scheduler on the hourly model: C4 K1s 12.6 vs 14.5 ms; for inference the ring wins there,
+    // 7.3 vs 10.2 ms)
+    long long thr = 148LL * 4 * 32 * (storing_states ? 2 : 3);
     if (const char* e = std::getenv("HBV_B200_LEAN_SMALL")) thr = std::atoll(e);
     return (long long)d.B * LNM <= thr;
 }
@@ -529,7 +566,7 @@ template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int RD>
 static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
-    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)RD * LBPB * LNM * ((3 + ND) | 1)) * sizeof(float);
+    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)RD * (8 + 32 * ND)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
     if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
     else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
@@ -544,7 +581,7 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 template <int VAR, bool BETAET, bool SIG, int LBPB, int RD>
 static int launch_fwd_lean_warm(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     d.BPB = LBPB;
-    const size_t smem = (size_t)RD * LBPB * LNM * 3 * sizeof(float);
+    const size_t smem = (size_t)RD * 8 * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
     hbv_fwd_lean_kernel<VAR, BETAET, 0, 0, SIG, false, LBPB, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
     count_launch();
@@ -556,7 +593,7 @@ static int launch_fwd_lean_warm(KDesc d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET>
 int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
-    if (!lean_common_ok(d) || !lean_small_grid(d)) return HBV_NOT_ELIGIBLE;   // large grids: K1 is as lean
+    if (!lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
     if (io.drop != nullptr || io.muwts != nullptr || io.state_series != nullptr || io.ckpt != nullptr)
         return HBV_NOT_ELIGIBLE;
     return d.apply_sigmoid ? launch_fwd_lean_warm<VAR, BETAET, true, 2, LRD_F>(d, io, st)
@@ -565,7 +602,7 @@ int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
-    if (lean_small_grid(d)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
+    if (lean_small_grid(d, io.ckpt != nullptr)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
     return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 
@@ -603,6 +640,8 @@ int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_
     if (!write_flux || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
     if (io.drop != nullptr || io.muwts != nullptr || io.state_series != nullptr) return HBV_NOT_ELIGIBLE;
     if (io.ckpt != nullptr && d.K != 1) return HBV_NOT_ELIGIBLE;
+    // the ring form copies the parameter runs 8 B at a time
+    if (lean_small_grid(d, io.ckpt != nullptr) && (d.dyn_ncol % 2 != 0 || reinterpret_cast<uintptr_t>(io.dyn) % 8 != 0)) return HBV_NOT_ELIGIBLE;
     for (int f = 0; f < Traits<VAR>::NFLUX; ++f)
         if (io.flux[f] == nullptr) return HBV_NOT_ELIGIBLE;
     const bool sig = d.apply_sigmoid != 0;
