@@ -26,6 +26,9 @@
 
 namespace hbv {
 
+#ifndef HBV_ADJ_BWD_MINB
+#define HBV_ADJ_BWD_MINB 5     // resident CTAs per SM the adjoint kernel's registers are sized for
+#endif
 constexpr int ADJ_NPAR = 13;
 constexpr int ADJ_TC = 8;       // time steps per output staging chunk
 
@@ -266,7 +269,7 @@ hbv_adj_fwd_kernel(const KDesc d, const AdjFwdPtrs io, const float tol, const in
 }
 
 template <bool BETAET, int DM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, HBV_ADJ_BWD_MINB)
 hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
     constexpr int NPAR = ADJ_NPAR;
     using DS = DynSet<NPAR, DM>;
