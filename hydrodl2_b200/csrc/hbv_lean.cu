@@ -276,6 +276,8 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // step are one contiguous run; the warp zeroes it with 8 B stores, __syncwarp(), then stores the
 // gradients on top — so the dense plane needs no memset (hbv_bwd_io_t.gdyn_zero_fill).
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false>
+// (one-warp form: registers unconstrained — 17 resident warps per SM; forcing 20-28 was measured
+// equal or slower on the 22.5k-basin shard, 4.31 / 5.55 / 5.72 ms: the kernel is HBM-bound there)
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
 hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     static_assert(!ZF || LBPB == 2, "fused zero fill needs a one-warp CTA");
