@@ -66,10 +66,11 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // K1s: forward.  CK: store the state before every step (K = 1) for the adjoint.
 // ================================================================================================
 // RD: 0 = inputs prefetched into registers (large grids: many resident warps hide HBM latency);
-// > 0 = per-thread shared-memory ring of RD steps filled with cp.async (small grids: one warp owns
-// a scheduler, only prefetch DISTANCE hides latency, and register loads cannot provide it — loads
-// in flight share the warp's six scoreboard slots, so waiting for the oldest waits for younger
-// ones too; ncu showed 55-64 % of all stall samples on the first use of a prefetched register)
+// > 0 = one-warp CTA with a shared-memory ring of RD steps filled with cp.async (small grids: one
+// warp owns a scheduler, only prefetch DISTANCE hides latency, and register loads cannot provide
+// it — loads in flight share the warp's six scoreboard slots, so waiting for the oldest waits for
+// younger ones too; ncu showed 55-64 % of all stall samples on the first use of a prefetched
+// register)
 // WF: write the flux planes (false: the warm-up / `initialize` run — states only, hbv.py:327-346)
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
