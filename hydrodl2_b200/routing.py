@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import _cabi as A
-from .ops import _check_cuda, _ptr, _stream, _timed
+from .ops import _check_cuda, _stream, _timed
 
 _TOPO_CACHE: dict = {}
 
