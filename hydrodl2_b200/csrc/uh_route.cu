@@ -270,10 +270,12 @@ using namespace hbv;
 extern "C" int hbv_b200_route_chunks(int32_t T, int32_t B) {
     if (T <= 0 || B <= 0) return 1;
     // one thread per (basin, time chunk): enough chunks to fill the 148 SMs (~1.5k threads
-    // each), but chunks of >= 32 steps so the lenF-1 halo re-read stays small
+    // each); a chunk is at least one MAXM-step block (the lenF-1 halo re-read then doubles the
+    // reads, which only small problems — where a thread's serial chunk is the whole latency of
+    // the launch — ever reach: C2 uses 46 chunks of 16 steps)
     const long long target = 148LL * 1536;
     int want = (int)((target + B - 1) / B);
-    int maxc = T / 32;
+    int maxc = (T + MAXM - 1) / MAXM;
     if (want > maxc) want = maxc;
     if (want < 1) want = 1;
     // chunk length is rounded up to a multiple of MAXM: recompute the chunk count it implies
