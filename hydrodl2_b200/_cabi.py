@@ -94,7 +94,7 @@ EXPORTS = (
     'hbv_b200_route_bwd', 'hbv_b200_abi_version', 'hbv_b200_last_error',
     'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
     'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd', 'hbv_b200_auto_ckpt',
-    'hbv_b200_dense_launches', 'hbv_b200_lean_launches',
+    'hbv_b200_dense_launches', 'hbv_b200_lean_launches', 'hbv_b200_workspace_bytes',
 )
 
 _LIB = None
@@ -126,6 +126,8 @@ def load():
     lib.hbv_b200_launch_count.restype = C.c_int64
     lib.hbv_b200_dense_launches.restype = C.c_int64
     lib.hbv_b200_lean_launches.restype = C.c_int64
+    lib.hbv_b200_workspace_bytes.restype = C.c_int64
+    lib.hbv_b200_workspace_bytes.argtypes = [C.POINTER(HbvDesc)]
     lib.hbv_b200_fwd.restype = C.c_int
     lib.hbv_b200_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvFwdIO), C.c_void_p]
     lib.hbv_b200_bwd.restype = C.c_int

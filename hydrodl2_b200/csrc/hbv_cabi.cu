@@ -97,6 +97,15 @@ int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
     return 16;
 }
 
+int64_t hbv_b200_workspace_bytes(const hbv_desc_t* desc) {
+    if (!desc) { hbv::set_error("null descriptor"); return HBV_E_NULL; }
+    if (desc->T <= 0 || desc->B <= 0 || desc->nmul <= 0) { hbv::set_error("non-positive dimension"); return HBV_E_SHAPE; }
+    if (desc->ckpt_interval < 0) { hbv::set_error("negative ckpt_interval"); return HBV_E_CKPT; }
+    const int K = desc->ckpt_interval > 0 ? desc->ckpt_interval : hbv_b200_auto_ckpt(desc->T, desc->B, desc->nmul);
+    const int64_t nseg = ((int64_t)desc->T + K - 1) / K;
+    return nseg * 5 * (int64_t)desc->B * desc->nmul * (int64_t)sizeof(float);
+}
+
 int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {
     if (!desc || !io) { hbv::set_error("null argument"); return HBV_E_NULL; }
     if (desc->variant == HBV_VARIANT_ADJ) { hbv::set_error("HBV_VARIANT_ADJ runs through hbv_b200_adj_fwd"); return HBV_E_VARIANT; }

@@ -309,6 +309,11 @@ HBV_API const char* hbv_b200_last_error(void);
  * 1 (store every state — 20 B per lane-step — and skip the adjoint's recompute pass) while the
  * stored states fit 16 GiB, 16 otherwise */
 HBV_API int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul);
+/* bytes of the caller-allocated state store (`ckpt`) hbv_b200_fwd writes and hbv_b200_bwd reads for
+ * this problem: ceil(T / K) * 5 * B * nmul floats with K = desc->ckpt_interval, or
+ * hbv_b200_auto_ckpt(T, B, nmul) when that is 0 (hbv_workspace_bytes).
+ * Returns < 0 (HBV_E_*) on a bad descriptor.  The library itself never allocates. */
+HBV_API int64_t hbv_b200_workspace_bytes(const hbv_desc_t* desc);
 /* number of kernels this library has launched in this process (bench accounting) */
 HBV_API int64_t hbv_b200_launch_count(void);
 /* how many of those were the TMA-staged kernels of hbv_dense.cu (K1d / K2d), which

@@ -117,6 +117,13 @@ def test_host_side_policies():
     assert lib.hbv_b200_auto_ckpt(730, 22500, 16) == 1         # north-star shard: 5.3 GB
     assert lib.hbv_b200_auto_ckpt(17520, 2500, 16) == 1        # C4 per GPU: 14 GB
     assert lib.hbv_b200_auto_ckpt(17520, 20000, 16) == 16      # C4 on one GPU: 112 GB
+    dsc = A.HbvDesc()
+    dsc.T, dsc.B, dsc.nmul, dsc.ckpt_interval = 730, 531, 16, 0
+    assert lib.hbv_b200_workspace_bytes(ctypes.byref(dsc)) == 730 * 5 * 531 * 16 * 4
+    dsc.ckpt_interval = 16
+    assert lib.hbv_b200_workspace_bytes(ctypes.byref(dsc)) == 46 * 5 * 531 * 16 * 4
+    dsc.T = 0
+    assert lib.hbv_b200_workspace_bytes(ctypes.byref(dsc)) < 0
     dev = torch.device('cpu')
     hbv = hydrodl2.load_model('hbv', ver_name='Hbv')({'dynamic_params': {'Hbv': ['parBETA', 'parBETAET']}, 'nmul': 16}, device=dev)
     p11 = hydrodl2.load_model('hbv_1_1p', ver_name='Hbv_1_1p')
