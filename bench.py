@@ -49,7 +49,7 @@ WORKLOADS = {
     # BASELINE.json configs[1]: the bench line
     'c2': dict(model='hbv', cls='Hbv', dyn=D2, n_par=13, nflux=11, warm_up=365, T=730, B=531,
                label='c2: hbv fwd+bwd training step'),
-    # north-star per-GPU shard (180k basins / 8 GPUs) of the same model: FP32-issue bound
+    # north-star per-GPU shard (180k basins / 8 GPUs) of the same model
     'shard': dict(model='hbv', cls='Hbv', dyn=D2, n_par=13, nflux=11, warm_up=365, T=730, B=22500,
                   label='shard: hbv fwd+bwd at the north-star per-GPU basin count'),
     # BASELINE.json configs[2], one GPU's share: hbv_1_1p, all 14 parameters dynamic: HBM bound
