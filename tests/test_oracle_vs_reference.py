@@ -77,3 +77,33 @@ def test_oracle_bit_exact_against_reference_hbv_2(ref, routing, seed):
         assert torch.equal(out[k], v.detach()), f'hbv_2 routing={routing}: {k} differs from the reference'
     assert torch.allclose(b0.grad, a0.grad, rtol=1e-6, atol=1e-9)
     assert torch.allclose(b1.grad, a1.grad, rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_bit_exact_against_reference_hbv_2_hourly(ref):
+    from oracle import hbv_oracle as O
+    T, n_units, n_gages = 96, 6, 2
+    dyn = ['parBETA', 'parK0', 'parBETAET']
+    g = torch.Generator().manual_seed(505)
+    x = O.synthetic_forcing(T, n_units, seed=505, hourly=True)
+    p0 = torch.rand(T, n_units, 3 * NMUL, generator=g)
+    p1 = torch.rand(n_units, 16 * NMUL, generator=g)
+    topo = torch.zeros(n_gages, n_units)
+    topo[0, :4] = 1
+    topo[1, 2:] = 1                       # units 2, 3 drain to both gages (nested)
+    p2 = torch.rand(int(topo.sum().item()), 3, generator=g)
+    xd = {'x_phy': x, 'ac_all': torch.rand(n_units, generator=g) * 5000,
+          'elev_all': torch.rand(n_units, generator=g) * 3500, 'outlet_topo': topo,
+          'areas': torch.rand(n_units, generator=g) * 99 + 1}
+    M = ref.load_model('hbv_2_hourly', ver_name='Hbv_2_hourly')
+    m = M({'dynamic_params': {'Hbv_2_hourly': dyn}, 'nmul': NMUL}, device=torch.device('cpu'))
+    a = [q.clone().requires_grad_(True) for q in (p0, p1, p2)]
+    torch.manual_seed(505)
+    out_ref = m(xd, a)
+    out_ref['streamflow'].sum().backward()
+    b = [q.clone().requires_grad_(True) for q in (p0, p1, p2)]
+    out, _ = O.forward_split('hbv_2_hourly', xd, b, nmul=NMUL, dynamic_params=dyn)
+    out['streamflow'].sum().backward()
+    for k in ('Qs', 'streamflow'):
+        assert torch.allclose(out[k], out_ref[k].detach(), rtol=1e-6, atol=1e-9), f'hourly: {k}'
+    for gb, ga in zip(b, a):
+        assert torch.allclose(gb.grad, ga.grad, rtol=1e-5, atol=1e-9)
