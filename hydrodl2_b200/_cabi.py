@@ -94,7 +94,8 @@ EXPORTS = (
     'hbv_b200_route_bwd', 'hbv_b200_abi_version', 'hbv_b200_last_error',
     'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
     'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd', 'hbv_b200_auto_ckpt',
-    'hbv_b200_dense_launches', 'hbv_b200_lean_launches', 'hbv_b200_workspace_bytes',
+    'hbv_b200_dense_launches', 'hbv_b200_lean_launches', 'hbv_b200_pipe_launches', 'hbv_b200_workspace_bytes',
+    'hbv_b200_set_option', 'hbv_b200_get_option', 'hbv_b200_fill_zero', 'hbv_b200_copy_cols',
 )
 
 _LIB = None
@@ -126,7 +127,16 @@ def load():
     lib.hbv_b200_launch_count.restype = C.c_int64
     lib.hbv_b200_dense_launches.restype = C.c_int64
     lib.hbv_b200_lean_launches.restype = C.c_int64
+    lib.hbv_b200_pipe_launches.restype = C.c_int64
     lib.hbv_b200_workspace_bytes.restype = C.c_int64
+    lib.hbv_b200_set_option.restype = C.c_int
+    lib.hbv_b200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    lib.hbv_b200_get_option.restype = C.c_int64
+    lib.hbv_b200_get_option.argtypes = [C.c_char_p]
+    lib.hbv_b200_fill_zero.restype = C.c_int
+    lib.hbv_b200_fill_zero.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.hbv_b200_copy_cols.restype = C.c_int
+    lib.hbv_b200_copy_cols.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.hbv_b200_workspace_bytes.argtypes = [C.POINTER(HbvDesc)]
     lib.hbv_b200_fwd.restype = C.c_int
     lib.hbv_b200_fwd.argtypes = [C.POINTER(HbvDesc), C.POINTER(HbvFwdIO), C.c_void_p]
@@ -163,6 +173,32 @@ def check(rc: int, what: str) -> None:
         msg = load().hbv_b200_last_error().decode(errors='replace')
         kind = 'CUDA error' if rc > 0 else 'argument error'
         raise RuntimeError(f'hydrodl2_b200.{what}: {kind} {rc}: {msg}')
+
+
+def set_option(name: str, value: int) -> None:
+    """Run-time experiment / test switch of the library (include/hbv_b200.h: hbv_b200_set_option);
+    value -1 restores the library's own policy."""
+    check(load().hbv_b200_set_option(name.encode(), int(value)), f'set_option({name})')
+
+
+def get_option(name: str) -> int:
+    return int(load().hbv_b200_get_option(name.encode()))
+
+
+class option:
+    """Context manager: `with option('lean', 0): ...` sets a switch and restores it on exit."""
+
+    def __init__(self, name: str, value: int):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = get_option(self.name)
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False
 
 
 def launch_count() -> int:

@@ -422,8 +422,8 @@ static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     if constexpr (DM >= 0) {
         constexpr int NSP = (RingSlots<Traits<VAR>::NPAR, DM>::FIRST_FREE + 6) | 1;
         const long long grid = (d.B + d.BPB - 1) / d.BPB;
-        const char* force = std::getenv("HBV_B200_RING");
-        const bool ring = force ? (force[0] == '1') : (grid * NT <= 148LL * 4 * 32 * 2);
+        const long long force = opt(OPT_RING);
+        const bool ring = force >= 0 ? (force == 1) : (grid * NT <= 148LL * 4 * 32 * 2);
         if (ring) {
             size_t bytes = 0;
             d.nstage = choose_nstage(NT, NSP, 1, stack, grid, &bytes);
@@ -439,7 +439,8 @@ static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     if (dm == 0) return launch_bwd_dm<VAR, BETAET, 0>(d, io, st);
     if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
         if (dm == DM_D2) {
-            const int rc = try_bwd_lean<VAR, BETAET, DM_D2>(d, io, st);              // hbv_lean.cu
+            int rc = try_bwd_pipe<VAR, BETAET, DM_D2>(d, io, st);                    // hbv_pipe.cu
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_bwd_lean<VAR, BETAET, DM_D2>(d, io, st);   // hbv_lean.cu
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
         }
     }
@@ -452,6 +453,7 @@ static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
         if (dm == DM_D3) {
             int rc = try_bwd_dense<VAR, BETAET, DM_D3>(d, io, st);
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_bwd_pipe<VAR, BETAET, DM_D3>(d, io, st);
             if (rc == HBV_NOT_ELIGIBLE) rc = try_bwd_lean<VAR, BETAET, DM_D3>(d, io, st);
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D3>(d, io, st);
         }

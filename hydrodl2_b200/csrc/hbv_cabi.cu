@@ -1,6 +1,7 @@
 // hbv_cabi.cu — extern "C" entry points, argument validation, error text, launch accounting.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "hbv_common.cuh"
 
@@ -10,6 +11,38 @@ static thread_local char g_err[256] = "";
 static std::atomic<long long> g_launches{0};
 static std::atomic<long long> g_dense_launches{0};
 static std::atomic<long long> g_lean_launches{0};
+static std::atomic<long long> g_pipe_launches{0};
+
+// option table: environment at first use, then hbv_b200_set_option
+static const char* const kOptNames[OPT_COUNT] = {
+    "LEAN", "PIPE", "PIPE_MAX", "RING", "LEAN_SMALL", "LEAN_BWD_RING", "DENSE", "DENSE_NS", "DENSE_NS_BWD",
+    "DENSE_MINB"};
+static std::atomic<long long> g_opt[OPT_COUNT];
+static std::atomic<int> g_opt_init{0};
+static void opt_init() {
+    if (g_opt_init.load(std::memory_order_acquire)) return;
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        char name[64];
+        std::snprintf(name, sizeof(name), "HBV_B200_%s", kOptNames[i]);
+        const char* e = std::getenv(name);
+        g_opt[i].store((e && *e) ? std::atoll(e) : -1, std::memory_order_relaxed);
+    }
+    g_opt_init.store(1, std::memory_order_release);
+}
+long long opt(Opt o) {
+    opt_init();
+    return g_opt[o].load(std::memory_order_relaxed);
+}
+static int opt_index(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        const char* a = kOptNames[i];
+        const char* b = name;
+        while (*a && *b && (*a == *b || *a == *b - 32)) { ++a; ++b; }   // case-insensitive on lower-case input
+        if (!*a && !*b) return i;
+    }
+    return -1;
+}
 
 void set_error(const char* msg) {
     std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
@@ -17,6 +50,7 @@ void set_error(const char* msg) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void count_dense_launch() { g_dense_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_lean_launch() { g_lean_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_pipe_launch() { g_pipe_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fwd_dispatch(const hbv_desc_t* desc, const hbv_fwd_io_t* io, cudaStream_t st);
 int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st);
@@ -85,6 +119,20 @@ const char* hbv_b200_last_error(void) { return hbv::g_err; }
 int64_t hbv_b200_launch_count(void) { return (int64_t)hbv::g_launches.load(); }
 int64_t hbv_b200_dense_launches(void) { return (int64_t)hbv::g_dense_launches.load(); }
 int64_t hbv_b200_lean_launches(void) { return (int64_t)hbv::g_lean_launches.load(); }
+int64_t hbv_b200_pipe_launches(void) { return (int64_t)hbv::g_pipe_launches.load(); }
+
+int hbv_b200_set_option(const char* name, int64_t value) {
+    const int i = hbv::opt_index(name);
+    if (i < 0) { hbv::set_error("unknown option"); return HBV_E_SHAPE; }
+    hbv::opt_init();
+    hbv::g_opt[i].store((long long)value, std::memory_order_relaxed);
+    return 0;
+}
+int64_t hbv_b200_get_option(const char* name) {
+    const int i = hbv::opt_index(name);
+    if (i < 0) { hbv::set_error("unknown option"); return INT64_MIN; }
+    return (int64_t)hbv::opt((hbv::Opt)i);
+}
 
 int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
     // Store every state (20 B per lane-step) whenever that fits 16 GiB of the 180 GB HBM: the

@@ -312,9 +312,35 @@ int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
 template <int VAR, bool BETAET>
 int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st);
 
+// ---- stage-pipelined kernels for the latency-bound regime (hbv_pipe.cu) ------------------------
+template <int VAR, bool BETAET, int DM>
+int try_fwd_pipe(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st);
+template <int VAR, bool BETAET, int DM>
+int try_bwd_pipe(const KDesc& d, const BwdPtrs& io, cudaStream_t st);
+template <int VAR, bool BETAET>
+int try_fwd_pipe_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st);
+
+// ---- experiment switches -----------------------------------------------------------------------
+// Read from the environment ONCE, when the library is first used (HBV_B200_<NAME>), and settable
+// at run time through hbv_b200_set_option("<name>", value) — no getenv on the dispatch path.
+// -1 = unset (the library's own policy decides).
+enum Opt {
+    OPT_LEAN = 0,         // 0: never the standard-layout kernels K1s / K2s (nor K1p / K2p)
+    OPT_PIPE,             // 0: never the stage-pipelined kernels K1p / K2p
+    OPT_PIPE_MAX,         // largest grid (lanes) K1p / K2p are used for
+    OPT_RING,             // 0 / 1: force the register / cp.async-ring input path of K1 / K2
+    OPT_LEAN_SMALL,       // grid size (lanes) up to which K1s uses its ring form
+    OPT_LEAN_BWD_RING,    // 0: K2s register form
+    OPT_DENSE,            // 0: never K1d / K2d, 2: wherever the shapes allow (tests), 1 / unset: where they win
+    OPT_DENSE_NS, OPT_DENSE_NS_BWD, OPT_DENSE_MINB,
+    OPT_COUNT
+};
+long long opt(Opt o);
+
 void set_error(const char* msg);
 void count_launch(int n = 1);
 void count_dense_launch();
 void count_lean_launch();
+void count_pipe_launch();
 
 }  // namespace hbv

@@ -522,8 +522,8 @@ static bool layout_matches(const KDesc& d) {
 // HBV_B200_DENSE: 0 = always K1 / K2, 2 = take the dense kernels whenever the shapes allow it
 // (tests), unset / 1 = where they win
 static int dense_mode() {
-    const char* e = std::getenv("HBV_B200_DENSE");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    const long long v = opt(OPT_DENSE);
+    return (v >= 0 && v <= 2) ? (int)v : 1;
 }
 
 // Common gate: compile-time dynamic set (dm > 0, no dropout), nmul 16, the dynamic columns are at
@@ -569,9 +569,9 @@ static int optin_smem(K k, size_t smem, std::atomic<int>* flag) {
     return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
+static int opt_int(Opt o, int dflt) {
+    const long long v = opt(o);
+    return v >= 0 ? (int)v : dflt;
 }
 
 template <int VAR, bool BETAET, int DM, int LAYOUT>
@@ -581,7 +581,7 @@ static int launch_fwd_dense(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     const DenseGeom g = dense_geom(d);
     const size_t fixed = 64 + g.tile_bytes;
     const size_t slot = g.pbytes + g.fbytes;
-    int ns = env_int("HBV_B200_DENSE_NS", 0);
+    int ns = opt_int(OPT_DENSE_NS, 0);
     if (ns <= 0) {
         ns = 8;                                   // deepest ring that still lets 4 CTAs share an SM
         while (ns > 4 && fixed + ns * slot > smem_budget_4cta()) ns -= DTC;
@@ -609,7 +609,7 @@ static int launch_bwd_dense_m(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     const DenseGeom g = dense_geom(d);
     const size_t fixed = 64 + 2 * (size_t)g.obytes;
     const size_t slot = g.pbytes + g.fbytes + g.gbytes + g.sbytes;
-    int ns = env_int("HBV_B200_DENSE_NS_BWD", 0);
+    int ns = opt_int(OPT_DENSE_NS_BWD, 0);
     if (ns <= 0) {
         ns = 6;
         const size_t budget = (size_t)(227 * 1024) / MINB - 1024;
@@ -632,7 +632,7 @@ static int launch_bwd_dense_m(KDesc d, const BwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT>
 static int launch_bwd_dense(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
-    const int m = env_int("HBV_B200_DENSE_MINB", 5);
+    const int m = opt_int(OPT_DENSE_MINB, 5);
     if (m == 6) return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 6>(d, io, st);
     if (m == 4) return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 4>(d, io, st);
     return launch_bwd_dense_m<VAR, BETAET, DM, LAYOUT, 5>(d, io, st);

@@ -258,8 +258,8 @@ static int launch_fwd_k(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     size_t tile = WRITE_FLUX ? (size_t)TC * d.BPB * tile_bstride(d.nmul) * sizeof(float) : 0;
     if constexpr (DM >= 0) {
         const long long grid = (d.B + d.BPB - 1) / d.BPB;
-        const char* force = std::getenv("HBV_B200_RING");     // 0 / 1: override (experiments)
-        const bool ring = force ? (force[0] == '1') : (grid * d.BPB * d.nmul <= 148LL * 4 * 32 * 2);
+        const long long force = opt(OPT_RING);     // 0 / 1: override (experiments)
+        const bool ring = force >= 0 ? (force == 1) : (grid * d.BPB * d.nmul <= 148LL * 4 * 32 * 2);
         if (ring) {
             size_t bytes = 0;
             d.nstage = choose_nstage(d.BPB * d.nmul, RCfg::NSP, RCfg::RC, tile, grid, &bytes);
@@ -279,7 +279,8 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
     const int dm = static_dynmask(d, io.drop != nullptr);
     if (!write_flux) {
         if (dm == 0) {
-            const int rc = try_fwd_lean_warm<VAR, BETAET>(d, io, st);              // hbv_lean.cu
+            int rc = try_fwd_pipe_warm<VAR, BETAET>(d, io, st);                    // hbv_pipe.cu
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_fwd_lean_warm<VAR, BETAET>(d, io, st);   // hbv_lean.cu
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, false, 0>(d, io, st);
         }
         return launch_fwd_k<VAR, BETAET, false, -1>(d, io, st);
@@ -287,7 +288,8 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
     if (dm == 0) return launch_fwd_k<VAR, BETAET, true, 0>(d, io, st);
     if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
         if (dm == DM_D2) {
-            const int rc = try_fwd_lean<VAR, BETAET, DM_D2>(d, io, true, st);       // hbv_lean.cu
+            int rc = try_fwd_pipe<VAR, BETAET, DM_D2>(d, io, true, st);             // hbv_pipe.cu
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_fwd_lean<VAR, BETAET, DM_D2>(d, io, true, st);   // hbv_lean.cu
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_D2>(d, io, st);
         }
     }
@@ -300,6 +302,7 @@ static int launch_fwd(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaSt
     if constexpr (VAR == HBV_VARIANT_HBV2 || VAR == HBV_VARIANT_HOURLY) {
         if (dm == DM_D3) {
             int rc = try_fwd_dense<VAR, BETAET, DM_D3>(d, io, true, st);
+            if (rc == HBV_NOT_ELIGIBLE) rc = try_fwd_pipe<VAR, BETAET, DM_D3>(d, io, true, st);
             if (rc == HBV_NOT_ELIGIBLE) rc = try_fwd_lean<VAR, BETAET, DM_D3>(d, io, true, st);
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_fwd_k<VAR, BETAET, true, DM_D3>(d, io, st);
         }

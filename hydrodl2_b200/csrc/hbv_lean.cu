@@ -530,11 +530,9 @@ static bool lean_layout_matches(const KDesc& d) {
 }
 
 static bool lean_common_ok(const KDesc& d) {
-    const char* e = std::getenv("HBV_B200_LEAN");        // 0: always K1 / K2 (A/B experiments)
-    if (e && e[0] == '0') return false;
+    if (opt(OPT_LEAN) == 0) return false;                // 0: always K1 / K2 (A/B experiments)
     if (d.nmul != LNM || d.nvar != 3 || d.i_prcp != 0 || d.i_tmean != 1 || d.i_pet != 2) return false;
-    const char* force = std::getenv("HBV_B200_RING");    // 1: keep the cp.async ring kernels (A/B)
-    return !(force && force[0] == '1');
+    return opt(OPT_RING) != 1;                           // 1: keep the cp.async ring kernels of K1 / K2 (A/B)
 }
 
 // Which form runs where (measured on B200, `hbv` D2, ms per kernel; forward = inference / training):
@@ -554,12 +552,11 @@ static bool lean_small_grid(const KDesc& d, bool storing_states = false) {
     // scheduler on the hourly model: C4 K1s 12.6 vs 14.5 ms; for inference the ring wins there,
     // 7.3 vs 10.2 ms)
     long long thr = 148LL * 4 * 32 * (storing_states ? 2 : 3);
-    if (const char* e = std::getenv("HBV_B200_LEAN_SMALL")) thr = std::atoll(e);
+    if (opt(OPT_LEAN_SMALL) >= 0) thr = opt(OPT_LEAN_SMALL);
     return (long long)d.B * LNM <= thr;
 }
 static bool lean_bwd_ring(const KDesc& d) {
-    const char* e = std::getenv("HBV_B200_LEAN_BWD_RING");
-    return !(e && e[0] == '0') && d.dyn_ncol % 2 == 0;      // (8 B copies of the parameter runs)
+    return opt(OPT_LEAN_BWD_RING) != 0 && d.dyn_ncol % 2 == 0;      // (8 B copies of the parameter runs)
 }
 
 constexpr int LRD_F = 12;    // small grids: forward ring depth (steps)

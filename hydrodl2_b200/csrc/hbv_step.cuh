@@ -84,32 +84,40 @@ __device__ __forceinline__ float flog(float a) { return 0.693147180559945f * lg2
 __device__ __forceinline__ float fexp(float a) { return ex2_approx(1.442695040888963f * a); }
 #endif
 
-// Forward step.  S = {SNOWPACK, MELTWATER, SM, SUZ, SLZ} updated in place.
-// P and PET are the forcing values as the step uses them (hourly: already / dt).
-// F[] receives the NFLUX per-lane fluxes in HBV_F_* order.
-template <int VAR, bool BETAET, bool TAPE>
-__device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<VAR>::NPAR],
-                                         float P, float T, float PET, const LaneConst& c,
-                                         float (&F)[HBV_MAX_FLUX], Tape& tp) {
+// ---- the step as three stages --------------------------------------------------------------
+// One HBV step is a feed-forward chain of three stages, each owning its states:
+//   snow  (SNOWPACK, MELTWATER)  -> RAIN, tosoil
+//   soil  (SM; reads SLZ through capillary rise in 1.1p / 2.0) -> recharge, excess, SLZa
+//   resp  (SUZ, SLZ)             -> Q0, Q1, Q2, PERC
+// The snow routine never reads soil or groundwater state, the soil routine reads the lower zone
+// only at its very end (capillary rise), so a kernel may run snow(t+2), soil(t+1) and resp(t) in
+// the same loop iteration as three independent dependency chains (hbv_pipe.cu); step_fwd /
+// step_bwd below run them back to back for one t.  Arithmetic and evaluation order inside a
+// stage follow the reference line by line.
+struct SoilOut { float recharge, excess, ET, ef, capillary, IE; };
+struct RespOut { float Q0, Q1, Q2, PERC; };
+
+// snow routine: hbv.py:428-459 (hourly: hbv_2_hourly.py:528-566).  SP, MW updated in place
+// (SP on exit is also the SWE series value).
+template <int VAR, bool TAPE>
+__device__ __forceinline__ void snow_fwd(float& SPio, float& MWio, const float (&p)[Traits<VAR>::NPAR],
+                                         float P, float T, const LaneConst& c,
+                                         float& RAIN, float& tosoil, Tape& tp) {
     using TR = Traits<VAR>;
-    const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
-    float SP = S[0], MW = S[1], SM = S[2], SUZ = S[3], SLZ = S[4];
-
+    const float dt = c.dt, inv_dt = c.inv_dt;
+    float SP = SPio, MW = MWio;
     if constexpr (TR::HOURLY) {  // hbv_2_hourly.py:528-533
-        if constexpr (TAPE) { tp.SPg = SP; tp.MWg = MW; tp.SMg = SM; tp.SUZg = SUZ; tp.SLZg = SLZ; }
+        if constexpr (TAPE) { tp.SPg = SP; tp.MWg = MW; }
         SP = fmaxf(SP, 0.f); MW = fmaxf(MW, 0.f);
-        SM = fmaxf(SM, nz); SUZ = fmaxf(SUZ, nz); SLZ = fmaxf(SLZ, nz);
     }
-
     float TTe = p[HBV_P_TT];
     if constexpr (TR::LAT) TTe = (c.Elev >= 2000.f) ? 4.0f : p[HBV_P_TT];  // hbv_2.py:473-475
     const bool israin = (T >= TTe);
-    const float RAIN = israin ? P : 0.f;
+    RAIN = israin ? P : 0.f;
     const float SNOW = (T < TTe) ? P : 0.f;
     const float dT = T - TTe;
 
-    // Snow -----------------------------------------------------------------------------------
-    float SP1, melt0, melt2, melt, MW1, SP2, rf0, rf2, rf, SP3, MW2, ts0, tosoil, MW3;
+    float SP1, melt0, melt2, melt, MW1, SP2, rf0, rf2, rf, SP3, MW2, ts0, MW3;
     if constexpr (TR::HOURLY) SP1 = SP + SNOW * dt; else SP1 = SP + SNOW;
     melt0 = p[HBV_P_CFMAX] * dT;
     melt2 = fmaxf(melt0, 0.f);
@@ -127,8 +135,28 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     if constexpr (TR::HOURLY) ts0 = ts0 * inv_dt;
     tosoil = fmaxf(ts0, 0.f);
     if constexpr (TR::HOURLY) MW3 = MW2 - tosoil * dt; else MW3 = MW2 - tosoil;
+    SPio = SP3; MWio = MW3;
+    if constexpr (TAPE) {
+        tp.TTe = TTe; tp.dT = dT;
+        tp.SP1 = SP1; tp.melt0 = melt0; tp.melt2 = melt2; tp.MW1 = MW1; tp.rf0 = rf0; tp.rf2 = rf2;
+        tp.SP3 = SP3; tp.ts0 = ts0;
+    }
+}
 
-    // Soil -----------------------------------------------------------------------------------
+// soil routine + capillary rise: hbv.py:462-480, hbv_1_1p.py:482-490, hbv_2_hourly.py:568-617.
+// SM updated in place; SLZ (variants with capillary rise only) enters as the lower-zone storage
+// at the start of the step and leaves as SLZ after capillary rise (the response stage's input).
+template <int VAR, bool BETAET, bool TAPE>
+__device__ __forceinline__ void soil_fwd(float& SMio, float& SLZio, const float (&p)[Traits<VAR>::NPAR],
+                                         float RAIN, float tosoil, float PET, const LaneConst& c,
+                                         SoilOut& o, Tape& tp) {
+    using TR = Traits<VAR>;
+    const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
+    float SM = SMio, SLZ = SLZio;
+    if constexpr (TR::HOURLY) {
+        if constexpr (TAPE) { tp.SMg = SM; tp.SLZg = SLZ; }
+        SM = fmaxf(SM, nz); SLZ = fmaxf(SLZ, nz);
+    }
     const float r = fdiv(SM, p[HBV_P_FC]);
     const float sw0 = pow_pos(r, p[HBV_P_BETA]);
     const float sw = fminf(fmaxf(sw0, 0.f), 1.f);
@@ -166,7 +194,7 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     if constexpr (TR::HOURLY) { ET = et2 * inv_dt; SMd = SM2 - ET * dt; } else SMd = SM2 - ET;
     const float SM3 = fmaxf(SMd, nz);
 
-    // Capillary rise (hbv_1_1p.py:482-490) -----------------------------------------------------
+    // Capillary rise (hbv_1_1p.py:482-490)
     float SMf = SM3, SLZa = SLZ, capillary = 0.f, r2 = 0.f, capf = 0.f, c1 = 0.f, SMc = 0.f, SLZc = 0.f;
     if constexpr (TR::CAP) {
         r2 = fdiv(SM3, p[HBV_P_FC]);
@@ -184,8 +212,33 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
         SMf = fmaxf(SMc, nz);
         SLZa = fmaxf(SLZc, nz);
     }
+    SMio = SMf;
+    if constexpr (TR::CAP) SLZio = SLZa;
+    o.recharge = recharge; o.excess = excess; o.ET = ET; o.ef = ef; o.capillary = capillary; o.IE = IE;
+    if constexpr (TAPE) {
+        tp.r = r; tp.sw0 = sw0; tp.sw = sw; tp.W = W; tp.infil = infil;
+        tp.s_base = s_base; tp.pw = pw; tp.fcap = fcap; tp.fmin = fmin;
+        tp.ex0 = ex0; tp.SM2 = SM2; tp.den = den; tp.ef0 = ef0; tp.ef1 = ef1; tp.ef = ef;
+        tp.et1 = et1; tp.SMd = SMd;
+        tp.r2 = r2; tp.capf = capf; tp.c1 = c1; tp.SLZin = SLZ; tp.SM3 = SM3;
+        tp.capillary = capillary; tp.SMc = SMc; tp.SLZc = SLZc;
+    }
+}
 
-    // Groundwater boxes (hbv.py:483-492) -------------------------------------------------------
+// response boxes: hbv.py:483-492, hbv_2.py:545-550 (lateral flux), hbv_2_hourly.py:619-648.
+// SUZ, SLZ updated in place (SLZ enters as the value after capillary rise).
+template <int VAR, bool TAPE>
+__device__ __forceinline__ void resp_fwd(float& SUZio, float& SLZio, const float (&p)[Traits<VAR>::NPAR],
+                                         float recharge, float excess, const LaneConst& c,
+                                         RespOut& o, Tape& tp) {
+    using TR = Traits<VAR>;
+    const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
+    float SUZ = SUZio;
+    const float SLZa = SLZio;
+    if constexpr (TR::HOURLY) {
+        if constexpr (TAPE) tp.SUZg = SUZ;
+        SUZ = fmaxf(SUZ, nz);
+    }
     float SUZ1, pc, PERC, SUZ2, q0a, Q0, SUZ3, Q1, SUZ4, SLZ1;
     if constexpr (TR::HOURLY) {
         SUZ1 = SUZ + (recharge + excess) * dt;
@@ -222,30 +275,35 @@ __device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<
     const float Q2 = p[HBV_P_K2] * SLZ2;
     float SLZ3;
     if constexpr (TR::HOURLY) SLZ3 = SLZ2 - Q2 * dt; else SLZ3 = SLZ2 - Q2;
-
-    S[0] = SP3; S[1] = MW3; S[2] = SMf; S[3] = SUZ4; S[4] = SLZ3;
-
-    float Qsim = Q0 + Q1 + Q2;
-    if constexpr (TR::HOURLY) Qsim = Qsim + IE;
-    F[HBV_F_QSIM] = Qsim; F[HBV_F_Q0] = Q0; F[HBV_F_Q1] = Q1; F[HBV_F_Q2] = Q2;
-    F[HBV_F_AET] = ET; F[HBV_F_SWE] = SP3; F[HBV_F_RECHARGE] = recharge; F[HBV_F_EXCS] = excess;
-    F[HBV_F_EVAPFACTOR] = ef; F[HBV_F_TOSOIL] = tosoil; F[HBV_F_PERC] = PERC;
-    F[HBV_F_CAPILLARY] = capillary;
-
+    SUZio = SUZ4; SLZio = SLZ3;
+    o.Q0 = Q0; o.Q1 = Q1; o.Q2 = Q2; o.PERC = PERC;
     if constexpr (TAPE) {
-        tp.TTe = TTe; tp.dT = dT;
-        tp.SP1 = SP1; tp.melt0 = melt0; tp.melt2 = melt2; tp.MW1 = MW1; tp.rf0 = rf0; tp.rf2 = rf2;
-        tp.SP3 = SP3; tp.ts0 = ts0;
-        tp.r = r; tp.sw0 = sw0; tp.sw = sw; tp.W = W; tp.infil = infil;
-        tp.s_base = s_base; tp.pw = pw; tp.fcap = fcap; tp.fmin = fmin;
-        tp.ex0 = ex0; tp.SM2 = SM2; tp.den = den; tp.ef0 = ef0; tp.ef1 = ef1; tp.ef = ef;
-        tp.et1 = et1; tp.SMd = SMd;
-        tp.r2 = r2; tp.capf = capf; tp.c1 = c1; tp.SLZin = SLZ; tp.SM3 = SM3;
-        tp.capillary = capillary; tp.SMc = SMc; tp.SLZc = SLZc;
         tp.SUZ1 = SUZ1; tp.pc = pc; tp.q0a = q0a; tp.SUZ3 = SUZ3; tp.SLZ1 = SLZ1;
         tp.lfarg = lfarg; tp.lfval = lfval;
         if constexpr (!TR::LAT) tp.SLZ2 = SLZ2;
     }
+}
+
+// Forward step.  S = {SNOWPACK, MELTWATER, SM, SUZ, SLZ} updated in place.
+// P and PET are the forcing values as the step uses them (hourly: already / dt).
+// F[] receives the NFLUX per-lane fluxes in HBV_F_* order.
+template <int VAR, bool BETAET, bool TAPE>
+__device__ __forceinline__ void step_fwd(float (&S)[5], const float (&p)[Traits<VAR>::NPAR],
+                                         float P, float T, float PET, const LaneConst& c,
+                                         float (&F)[HBV_MAX_FLUX], Tape& tp) {
+    using TR = Traits<VAR>;
+    float RAIN, tosoil;
+    SoilOut so;
+    RespOut ro;
+    snow_fwd<VAR, TAPE>(S[0], S[1], p, P, T, c, RAIN, tosoil, tp);
+    soil_fwd<VAR, BETAET, TAPE>(S[2], S[4], p, RAIN, tosoil, PET, c, so, tp);
+    resp_fwd<VAR, TAPE>(S[3], S[4], p, so.recharge, so.excess, c, ro, tp);
+    float Qsim = ro.Q0 + ro.Q1 + ro.Q2;
+    if constexpr (TR::HOURLY) Qsim = Qsim + so.IE;
+    F[HBV_F_QSIM] = Qsim; F[HBV_F_Q0] = ro.Q0; F[HBV_F_Q1] = ro.Q1; F[HBV_F_Q2] = ro.Q2;
+    F[HBV_F_AET] = so.ET; F[HBV_F_SWE] = S[0]; F[HBV_F_RECHARGE] = so.recharge; F[HBV_F_EXCS] = so.excess;
+    F[HBV_F_EVAPFACTOR] = so.ef; F[HBV_F_TOSOIL] = tosoil; F[HBV_F_PERC] = ro.PERC;
+    F[HBV_F_CAPILLARY] = so.capillary;
 }
 
 // d/d{a,b} of min(a, b) with PyTorch's tie rule: returns weight on `a` (b gets 1 - w).
@@ -253,29 +311,23 @@ __device__ __forceinline__ float min_w(float a, float b) {
     return (a < b) ? 1.f : ((a > b) ? 0.f : 0.5f);
 }
 
-// Adjoint step.  On entry gS = dL/d(state after the step); gF = dL/d(per-lane fluxes of the
-// step).  On exit gS = dL/d(state before the step), gp[i] += dL/d(parameter i at this step) and
-// gX = dL/d(P, T, PET) of this step as the step uses them (hourly: P, PET already / dt).
-template <int VAR, bool BETAET>
-__device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_MAX_FLUX],
-                                         const float (&p)[Traits<VAR>::NPAR], float PET,
-                                         const LaneConst& c, const Tape& tp,
-                                         float (&gp)[Traits<VAR>::NPAR], float (&gX)[3]) {
+// ---- adjoint stages (reverse order: resp -> soil -> snow) -------------------------------------
+// resp_bwd: in  gSUZ (= dL/dSUZ after the step), gSLZ (= dL/dSLZ after the step), gF;
+//           out gSUZ (before the step), gSLZ = dL/dSLZa (the soil stage's output), and
+//           gRE = d(SUZ1)-path gradient shared by recharge and excess (already "* dt").
+template <int VAR>
+__device__ __forceinline__ void resp_bwd(float& gSUZ, float& gSLZ, const float (&gF)[HBV_MAX_FLUX],
+                                         const float (&p)[Traits<VAR>::NPAR], const LaneConst& c,
+                                         const Tape& tp, float (&gp)[Traits<VAR>::NPAR], float& gRE) {
     using TR = Traits<VAR>;
     const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
     auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };       // "* dt"
     auto ID = [&](float x) { return TR::HOURLY ? x * inv_dt : x; };  // "/ dt"
-
-    float gQ0 = gF[HBV_F_Q0] + gF[HBV_F_QSIM];
-    float gQ1 = gF[HBV_F_Q1] + gF[HBV_F_QSIM];
-    float gQ2 = gF[HBV_F_Q2] + gF[HBV_F_QSIM];
-    const float gIE = gF[HBV_F_QSIM];
-    float gSP3 = gS[0] + gF[HBV_F_SWE];
-    const float gMW3 = gS[1];
-    const float gSMf = gS[2];
-    const float gSUZ4 = gS[3];
-    const float gSLZ3 = gS[4];
-
+    const float gQ0 = gF[HBV_F_Q0] + gF[HBV_F_QSIM];
+    const float gQ1 = gF[HBV_F_Q1] + gF[HBV_F_QSIM];
+    const float gQ2 = gF[HBV_F_Q2] + gF[HBV_F_QSIM];
+    const float gSUZ4 = gSUZ;
+    const float gSLZ3 = gSLZ;
     // SLZ3 = SLZ2 - Q2*dt ; Q2 = K2*SLZ2
     const float SLZ2c = TR::LAT ? fmaxf(tp.SLZ2, 0.f) : tp.SLZ2;
     const float gQ2t = gQ2 - D(gSLZ3);
@@ -293,7 +345,6 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
         }
     }
     // SLZ1 = SLZa + PERC*dt
-    const float gSLZa = gSLZ1;
     float gPERC = gF[HBV_F_PERC] + D(gSLZ1);
     // SUZ4 = SUZ3 - Q1*dt ; Q1 = K1*SUZ3
     const float gQ1t = gQ1 - D(gSUZ4);
@@ -312,9 +363,29 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     const float gSUZ1 = gSUZ2 + gmin * wS;
     gp[HBV_P_PERC] += D(gmin * (1.f - wS));
     // SUZ1 = SUZ + (recharge + excess)*dt
-    const float gSUZ_in = gSUZ1;
-    float gRech = gF[HBV_F_RECHARGE] + D(gSUZ1);
-    float gExc = gF[HBV_F_EXCS] + D(gSUZ1);
+    gRE = D(gSUZ1);
+    gSUZ = gSUZ1;
+    if constexpr (TR::HOURLY) gSUZ = (tp.SUZg >= nz) ? gSUZ : 0.f;   // guard rail
+    gSLZ = gSLZ1;
+}
+
+// soil_bwd: in  gSM (= dL/dSM after the step), gSLZa (from resp_bwd), gRE, gF;
+//           out gSM (before the step), gSLZ (= dL/dSLZ at the start of the step: variants without
+//           capillary rise pass gSLZa through), gW = dL/d(RAIN + tosoil), gPET.
+template <int VAR, bool BETAET>
+__device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, const float (&gF)[HBV_MAX_FLUX],
+                                         const float (&p)[Traits<VAR>::NPAR], float PET, const LaneConst& c,
+                                         const Tape& tp, float (&gp)[Traits<VAR>::NPAR],
+                                         float& gW, float& gPET) {
+    using TR = Traits<VAR>;
+    const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
+    auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };
+    auto ID = [&](float x) { return TR::HOURLY ? x * inv_dt : x; };
+    const float gIE = gF[HBV_F_QSIM];
+    const float gSMf = gSM;
+    const float gSLZa = gSLZ;
+    float gRech = gF[HBV_F_RECHARGE] + gRE;
+    float gExc = gF[HBV_F_EXCS] + gRE;
 
     // Capillary
     float gSM3, gSLZ_in;
@@ -350,7 +421,7 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     gSM2 += get2 * wE;
     const float get0 = D(get2 * (1.f - wE));
     const float gef = gF[HBV_F_EVAPFACTOR] + get0 * PET;
-    gX[2] = get0 * tp.ef;                                  // d/dPET (as the step uses it)
+    gPET = get0 * tp.ef;                                   // d/dPET (as the step uses it)
     const float gef1 = (tp.ef1 >= 0.f && tp.ef1 <= 1.f) ? gef : 0.f;
     float gef0 = gef1;
     if constexpr (BETAET) {
@@ -376,7 +447,7 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     // recharge = infil*sw
     ginfil += gRech * tp.sw;
     const float gsw = gRech * tp.infil;
-    float gW, gr = 0.f;
+    float gr = 0.f;
     if constexpr (TR::HOURLY) {
         // infil = min(W, fcap) ; IE = max(W - fcap, 0)
         const float wW = min_w(tp.W, tp.fcap);
@@ -401,6 +472,28 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     const float qr = fdiv(gr, p[HBV_P_FC]);
     gSM_in += qr;
     gp[HBV_P_FC] -= qr * tp.r;
+    gSM = gSM_in;
+    gSLZ = gSLZ_in;
+    if constexpr (TR::HOURLY) {  // guard rails: clamp(x, min=m) passes where x >= m
+        gSM = (tp.SMg >= nz) ? gSM : 0.f;
+        gSLZ = (tp.SLZg >= nz) ? gSLZ : 0.f;
+    }
+}
+
+// snow_bwd: in  gSP (= dL/dSNOWPACK after the step, the SWE series' cotangent NOT yet added),
+//           gMW (after the step), gW (from soil_bwd), gF; out gSP, gMW before the step,
+//           gP = dL/dP, gT = dL/dT.
+template <int VAR>
+__device__ __forceinline__ void snow_bwd(float& gSP, float& gMW, float gW, const float (&gF)[HBV_MAX_FLUX],
+                                         const float (&p)[Traits<VAR>::NPAR], const LaneConst& c,
+                                         const Tape& tp, float (&gp)[Traits<VAR>::NPAR],
+                                         float& gP, float& gT) {
+    using TR = Traits<VAR>;
+    const float dt = c.dt, inv_dt = c.inv_dt;
+    auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };
+    auto ID = [&](float x) { return TR::HOURLY ? x * inv_dt : x; };
+    float gSP3 = gSP + gF[HBV_F_SWE];
+    const float gMW3 = gMW;
     // W = RAIN + tosoil ; MW3 = MW2 - tosoil*dt ; tosoil = max(ts0, 0) ; ts0 = (MW2 - CWH*SP3)/dt
     const float gtosoil = gF[HBV_F_TOSOIL] + gW - D(gMW3);
     const float gx = (tp.ts0 >= 0.f) ? ID(gtosoil) : 0.f;
@@ -429,17 +522,27 @@ __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_M
     else gp[HBV_P_TT] += gTTe;
     // forcings: T enters as T - TTe only (the rain/snow masks carry no gradient);
     // P = RAIN (T >= TTe, into W) or SNOW (T < TTe, into SP1 = SP + SNOW*dt)
-    gX[1] = -gTTe;
-    gX[0] = (tp.dT >= 0.f) ? gW : D(gSP1);
-
-    gS[0] = gSP1; gS[1] = gMW_in; gS[2] = gSM_in; gS[3] = gSUZ_in; gS[4] = gSLZ_in;
-    if constexpr (TR::HOURLY) {  // guard rails: clamp(x, min=m) passes where x >= m
-        gS[0] = (tp.SPg >= 0.f) ? gS[0] : 0.f;
-        gS[1] = (tp.MWg >= 0.f) ? gS[1] : 0.f;
-        gS[2] = (tp.SMg >= nz) ? gS[2] : 0.f;
-        gS[3] = (tp.SUZg >= nz) ? gS[3] : 0.f;
-        gS[4] = (tp.SLZg >= nz) ? gS[4] : 0.f;
+    gT = -gTTe;
+    gP = (tp.dT >= 0.f) ? gW : D(gSP1);
+    gSP = gSP1; gMW = gMW_in;
+    if constexpr (TR::HOURLY) {
+        gSP = (tp.SPg >= 0.f) ? gSP : 0.f;
+        gMW = (tp.MWg >= 0.f) ? gMW : 0.f;
     }
+}
+
+// Adjoint step.  On entry gS = dL/d(state after the step); gF = dL/d(per-lane fluxes of the
+// step).  On exit gS = dL/d(state before the step), gp[i] += dL/d(parameter i at this step) and
+// gX = dL/d(P, T, PET) of this step as the step uses them (hourly: P, PET already / dt).
+template <int VAR, bool BETAET>
+__device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_MAX_FLUX],
+                                         const float (&p)[Traits<VAR>::NPAR], float PET,
+                                         const LaneConst& c, const Tape& tp,
+                                         float (&gp)[Traits<VAR>::NPAR], float (&gX)[3]) {
+    float gRE, gW;
+    resp_bwd<VAR>(gS[3], gS[4], gF, p, c, tp, gp, gRE);
+    soil_bwd<VAR, BETAET>(gS[2], gS[4], gRE, gF, p, PET, c, tp, gp, gW, gX[2]);
+    snow_bwd<VAR>(gS[0], gS[1], gW, gF, p, c, tp, gp, gX[0], gX[1]);
 }
 
 __device__ __forceinline__ void init_lane_const(LaneConst& lc, float Ac, float Elev) {

@@ -21,6 +21,7 @@ import torch
 
 from ... import _cabi as A
 from ...ops import RunSpec, hbv_run, hbv_states_only, start_grad_plane
+from ._seam import PackedSeam
 
 _FLUX_KEYS = (
     # (dict key, source) — source: ('r', i) routed plane i, ('f', slot) flux slot, 'pet'
@@ -34,7 +35,7 @@ _FLUX_KEYS = (
 )
 
 
-class PackedHbv(torch.nn.Module):
+class PackedHbv(PackedSeam, torch.nn.Module):
     """Base of `Hbv` and `Hbv_1_1p` (packed raw parameter tensor + sigmoid)."""
 
     _variant = A.VARIANT_HBV
@@ -175,6 +176,20 @@ class PackedHbv(torch.nn.Module):
                     anyset = anyset or bool(dr.any())
         return mask.to(self.device) if anyset else None
 
+    def io_footprint(self, n_rows: int) -> dict:
+        """Which entries of a `parameters` tensor [n_rows, B, ncol] this model's kernels read
+        ('read') and which entries of its dense gradient can be non-zero ('grad') — for
+        column-sparse host staging (hydrodl2_b200.hostio.sparse_copy).  Time-varying parameters
+        are read at every run row (hbv.py:236-246); everything else only at the last row
+        (static values, hbv.py:242; routing, hbv.py:212-214) and, for the no-grad warm-up, at
+        its last row (hbv.py:329-332)."""
+        names = list(self.parameter_bounds.keys())
+        warm = self.warm_up if self.warm_up_states else 0
+        blocks = [(i * self.nmul, self.nmul) for i, nm in enumerate(names) if nm in self.dynamic_params]
+        rows = sorted({n_rows - 1} | ({warm - 1} if warm > 0 else set()))
+        return {'read': {'rows_full': rows, 'col_blocks': blocks, 'row_range': (warm, n_rows)},
+                'grad': {'rows_full': [n_rows - 1], 'col_blocks': blocks, 'row_range': (warm, n_rows)}}
+
     # ------------------------------------------------------------------ forward
     def forward(
         self,
@@ -205,6 +220,9 @@ class PackedHbv(torch.nn.Module):
 
         parameters = parameters.contiguous()
         x = x.contiguous()
+        if self.routing:     # `routing_param_dict` (hbv.py:311-312), materialised only if someone reads it
+            n_phy = len(self.parameter_bounds) * self.nmul
+            self._remember_routing(lambda p=parameters.detach(): torch.sigmoid(p[-1, :, n_phy:n_phy + 2]))
         spec = self._spec(self.dynamic_params, self.routing)
         gplane = None
         if warm_up > 0:

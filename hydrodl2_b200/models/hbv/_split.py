@@ -17,6 +17,7 @@ import torch
 
 from ... import _cabi as A
 from ...ops import RunSpec, hbv_run, hbv_states_only
+from ._seam import SplitSeam
 
 _BASE_BOUNDS = {
     'parBETA': [1.0, 6.0], 'parFC': [50, 1000], 'parK0': [0.05, 0.9], 'parK1': [0.01, 0.5],
@@ -33,7 +34,7 @@ _FLUX = (
 )
 
 
-class SplitHbv(torch.nn.Module):
+class SplitHbv(SplitSeam, torch.nn.Module):
     """Base of `Hbv_2` and `Hbv_2_hourly`."""
 
     _variant = A.VARIANT_HBV2
@@ -183,6 +184,9 @@ class SplitHbv(torch.nn.Module):
         sta = parameters[1]
         if dyn is not None and dyn.shape[-1] == 0:
             dyn = None
+        if self.routing:     # `routing_param_dict` (hbv_2.py:349-350), materialised only if someone reads it
+            rc = self._route_col()
+            self._remember_routing(lambda s_=sta.detach(): s_[:, rc:rc + 2])
         if states is not None:
             current = torch.stack(tuple(states))
         elif (not self.states) or (not self.cache_states):
@@ -205,11 +209,11 @@ class SplitHbv(torch.nn.Module):
     def _run(self, x, dyn, sta, current, attrs, drop, routing):
         if self.comprout:
             raise RuntimeError('comprout=True is not supported (it fails in the reference as well)')
-        if routing and self.lenF > 16:
-            raise NotImplementedError(
-                'per-unit UH routing with lenF > 16 (routing=True on the hourly model) is not '
-                'implemented; the hourly model routes through distr_routing (use_distr_routing)')
-        spec = self._spec(routing)
+        # per-unit UH routing with more than 16 taps (the hourly model's lenF = 72,
+        # hbv_2_hourly.py:684-705) runs after the recurrence through the shared-memory-staged
+        # convolution of csrc/pair_route.cu (routing.unit_routing); <= 16 taps stay fused (K4)
+        long_uh = routing and self.lenF > 16 and not self.initialize
+        spec = self._spec(routing and not long_uh)
         if self.initialize:
             # hbv_2.py:630-632: only the storages are returned
             with torch.no_grad():
@@ -217,7 +221,24 @@ class SplitHbv(torch.nn.Module):
                 out = hbv_states_only(spec, x, None if dyn is None else dyn.detach().contiguous(),
                                       sta.detach().contiguous(), current, drop=drop, attrs=attrs)
             return {'flux': None, 'routed': None, 'bfi': None, 'state_out': out, 'series': None}
-        return hbv_run(spec, x, dyn, sta, current, drop=drop, attrs=attrs, muwts=self.muwts)
+        res = hbv_run(spec, x, dyn, sta, current, drop=drop, attrs=attrs, muwts=self.muwts)
+        if long_uh:
+            rc = self._route_col()
+            self._apply_long_uh(res, x.shape[0], sta[:, rc:rc + 2],
+                                tuple(tuple(v) for v in self.routing_parameter_bounds.values()))
+        return res
+
+    def _apply_long_uh(self, res, T, route_ab, bounds) -> None:
+        from ...routing import unit_routing
+        n_r = 1 if self._variant == A.VARIANT_HOURLY else 4
+        series = (A.F_QSIM, A.F_Q0, A.F_Q1, A.F_Q2)[:n_r]
+        res['routed'] = [unit_routing(res['flux'][f], route_ab, min(self.lenF, T), bounds) for f in series]
+        if self._variant != A.VARIANT_HOURLY:
+            res['bfi'] = 100 * (res['routed'][3].sum(0) / (res['routed'][0].sum(0) + self.nearzero))
+
+    def _route_col(self) -> int:
+        """First routing column of the static tensor (after the static physical parameters)."""
+        return (len(self.parameter_bounds) - len(self.dynamic_params)) * self.nmul
 
     # ------------------------------------------------------------------ seam
     def _PBM(self, forcing, Ac, Elevation, states, phy_dy_params_dict, phy_static_params_dict,
@@ -240,11 +261,16 @@ class SplitHbv(torch.nn.Module):
             self.dynamic_params, self.dy_drop = keep
         n = len(names)
         spec.par_lo, spec.par_hi = [0.0] * n, [1.0] * n
+        long_uh = None
         if spec.routing:
             ra = self.routing_param_dict['route_a'].view(-1, 1)
             rb = self.routing_param_dict['route_b'].view(-1, 1)
-            sta = torch.cat([sta, ra, rb], dim=1).contiguous()
-            spec.route_bounds = ((0.0, 1.0), (0.0, 1.0))
+            if self.lenF > 16 and not self.initialize:
+                long_uh = torch.cat([ra, rb], dim=1)          # already descaled: identity bounds
+                spec.routing = False
+            else:
+                sta = torch.cat([sta, ra, rb], dim=1).contiguous()
+                spec.route_bounds = ((0.0, 1.0), (0.0, 1.0))
         attrs = torch.stack([Ac.reshape(Ac.shape[0], -1)[:, 0], Elevation.reshape(Elevation.shape[0], -1)[:, 0]])
         attrs = attrs.to(self.device, dtype=torch.float32).contiguous()
         current = torch.stack(tuple(states))
@@ -256,6 +282,8 @@ class SplitHbv(torch.nn.Module):
                                       current, attrs=attrs)
             return {}, tuple(out[i].unsqueeze(0) for i in range(5))
         res = hbv_run(spec, x, dyn, sta, current, attrs=attrs, muwts=self.muwts)
+        if long_uh is not None:
+            self._apply_long_uh(res, x.shape[0], long_uh, ((0.0, 1.0), (0.0, 1.0)))
         series = (tuple(res['series'][i] for i in range(5)) if res['series'] is not None
                   else tuple(res['state_out'][i].unsqueeze(0) for i in range(5)))
         return self._flux_from_run(res, x, outlet_topo, areas, distr_params_dict), series

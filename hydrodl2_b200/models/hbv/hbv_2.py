@@ -51,7 +51,8 @@ class Hbv_2(SplitHbv):
             out[key] = flux[slot].unsqueeze(-1)
         out['BFI'] = bfi
         if not self.warm_up_states:
-            self.pred_cutoff = self.warm_up
+            # hbv_2.py:666-669 slices with `pred_cutoff`, which the 2.0 models never set (it stays
+            # 0): with warm_up_states=False the reference returns all T rows — so does this.
             for key in out:
                 if key != 'BFI':
                     out[key] = out[key][self.pred_cutoff:, :, :]

@@ -80,7 +80,7 @@ class Hbv_2_hourly(SplitHbv):
         qs = (res['routed'][0] if res['routed'] is not None else res['flux'][A.F_QSIM])
         out = {'Qs': qs.unsqueeze(-1) * self.dt}
         if not self.warm_up_states:
-            self.pred_cutoff = self.warm_up
+            # hbv_2_hourly.py:761-764: `pred_cutoff` is never set by the hourly model (stays 0)
             out['Qs'] = out['Qs'][self.pred_cutoff:, :, :]
         if self.use_distr_routing:
             from ...routing import distr_routing
@@ -95,9 +95,9 @@ class Hbv_2_hourly(SplitHbv):
                 qs_history = torch.cat(self._qs_buffer, dim=0)
             else:
                 qs_history = out['Qs']
-            rout = distr_routing(qs_history, distr, outlet_topo.to(self.device),
-                                 areas.to(self.device), lenF=self.lenF, lag_uh=self.lag_uh,
-                                 bounds=bounds)
+            # (the caller's own tensors key the topology cache; the index is built on the device)
+            rout = distr_routing(qs_history, distr, outlet_topo, areas, lenF=self.lenF,
+                                 lag_uh=self.lag_uh, bounds=bounds)
             out['streamflow'] = rout[-1:] if self.cache_states else rout
         return out
 
@@ -107,6 +107,6 @@ class Hbv_2_hourly(SplitHbv):
         from ...routing import distr_routing
         names = list(self.distr_parameter_bounds.keys())
         par = torch.stack([distr_params_dict[k] for k in names], dim=1)
-        rout = distr_routing(Qs, par, outlet_topo.to(Qs.device), areas.to(Qs.device), lenF=self.lenF,
+        rout = distr_routing(Qs, par, outlet_topo, areas, lenF=self.lenF,
                              lag_uh=self.lag_uh, bounds=tuple((0.0, 1.0) for _ in names))
         return {'Qs_rout': rout}

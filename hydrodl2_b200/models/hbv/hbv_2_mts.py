@@ -154,7 +154,9 @@ class Hbv_2_mts(torch.nn.Module):
         from ...routing import distr_routing
         bounds = tuple(tuple(v) for v in high.distr_parameter_bounds.values())
         distr = parameters[1][2].to(device)
-        topo_d, areas_d = topo.to(device), x_dict['areas'].to(device)
+        # the caller's own tensors key the topology cache (routing.pair_index); the index arrays
+        # are built on the device once and reused by every temporal chunk and every later call
+        topo_d, areas_d = topo, x_dict['areas']
         w = self.train_warmup
         routed = []
         for t in range(w, n_t, self.simulate_temporal_chunk_size):

@@ -54,6 +54,11 @@ def _fused_zero_fill(spec, dyn_ncol, n_basins) -> bool:
     # single warp's critical path and cost more than the in-order memset, 0.57 vs 0.56 ms)
     return spec.nmul == 16 and dyn_ncol % 2 == 0 and n_basins * spec.nmul > _SMALL_GRID_LANES
 
+# small grids: zero the gradient plane with the library's thin fill kernel on the side stream
+# instead of a memset in stream order.  Off by default — measured on B200 (C2): even a fill that
+# issues next to no instructions (TMA bulk stores, csrc/fill.cu) slows the latency-bound recurrence
+# kernels it runs next to through the memory system; graph-replayed step 0.77 vs 0.47 ms.
+THIN_FILL = os.environ.get('HBV_B200_THIN_FILL', '0') == '1'
 _SIDE_STREAMS = {}
 _SMALL_GRID_LANES = 148 * 4 * 32 * 2      # same boundary as the kernels' small-grid regime
 
@@ -220,11 +225,30 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0,
         else:
             gbuf.zero_()
 
-    if dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES:
-        # Latency-bound regime (a warp or two per scheduler): a full-occupancy fill running next to
-        # the recurrence kernels starves them for longer than the fill itself takes (C2: a 76 us
-        # memset stretched the 88 us warm-up kernel to 275 us) — zero in stream order instead.
-        fill()
+    small = dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES
+    if small and THIN_FILL:
+        # Latency-bound regime (a warp or two per scheduler): a full-occupancy memset running next
+        # to the recurrence kernels starves them for longer than the fill itself takes (C2: a 76 us
+        # memset stretched the 88 us warm-up kernel to 275 us), and in stream order it is 76 us of
+        # the critical path.  The library's thin fill (csrc/fill.cu: one warp per SM streaming TMA
+        # bulk stores of a zeroed shared-memory buffer, next to no instruction issue) runs on the
+        # side stream underneath the warm-up and forward kernels instead.
+        lib = A.load()
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            rows = t_off if fused else dyn.shape[0]
+            nbytes = rows * dyn.shape[1] * dyn.shape[2] * 4
+            with _timed('grad_plane_fill', dev):
+                A.check(lib.hbv_b200_fill_zero(gbuf.data_ptr(), nbytes, 0, side.cuda_stream), 'fill_zero')
+            if fused and spec.n_par * spec.nmul < dyn.shape[-1]:
+                gbuf[dyn.shape[0] - 1, :, spec.n_par * spec.nmul:].zero_()
+            gev = torch.cuda.Event()
+            gev.record(side)
+        return gbuf, gev, fused
+    if small:
+        fill()      # (HBV_B200_THIN_FILL=0: the round-1 behaviour, a memset in stream order)
         return gbuf, None, fused
     cur = torch.cuda.current_stream(dev)
     side = _side_stream(dev)

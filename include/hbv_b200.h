@@ -323,6 +323,31 @@ HBV_API int64_t hbv_b200_dense_launches(void);
 /* ... and how many were the standard-layout kernels of hbv_lean.cu (K1s / K2s), selected the same
  * way for the shipped dynamic sets on large grids (HBV_B200_LEAN=0 keeps K1 / K2) */
 HBV_API int64_t hbv_b200_lean_launches(void);
+/* Zero `nbytes` bytes at `ptr` (device memory) with a thin kernel: `n_ctas` one-warp CTAs (0 =
+ * one per SM) streaming TMA bulk stores from a zeroed shared-memory buffer.  Made for zeroing the
+ * dense parameter-gradient plane on a side stream underneath latency-bound kernels (csrc/fill.cu);
+ * replaces the cudaMemsetAsync the torch side would otherwise issue for torch.zeros_like. */
+HBV_API int hbv_b200_fill_zero(void* ptr, int64_t nbytes, int32_t n_ctas, void* stream);
+/* Copy the [rows x ncols] float block at column `col0` of a row-major [rows, row_stride] matrix
+ * from `src` to `dst` (same layout on both sides).  Either pointer may be mapped pinned HOST
+ * memory (cudaHostAlloc / torch pin_memory under UVA): the GPU then reads or writes it directly
+ * over PCIe, so a training loop stages only the column blocks the kernels read (the dynamic
+ * parameters of hbv.py:201-208) and fetches only the non-zero blocks of the gradient.  Used by
+ * hydrodl2_b200.hostio. */
+HBV_API int hbv_b200_copy_cols(float* dst, const float* src, int64_t rows, int64_t row_stride,
+                               int32_t col0, int32_t ncols, void* stream);
+/* Experiment / test switches.  Each is read from the environment (HBV_B200_<NAME>) once, when
+ * the library is first used, and can be changed at run time here; value -1 = unset (the
+ * library's own measured policy decides).  Names (case-insensitive): "lean" (0: never K1s / K2s /
+ * K1p / K2p), "pipe" (0: never K1p / K2p), "pipe_max" (largest grid in lanes for K1p / K2p),
+ * "ring" (0 / 1: force register / cp.async-ring inputs in K1 / K2), "lean_small",
+ * "lean_bwd_ring", "dense" (0: never K1d / K2d, 2: wherever the shapes allow), "dense_ns",
+ * "dense_ns_bwd", "dense_minb".  Returns 0, or HBV_E_SHAPE for an unknown name
+ * (get: INT64_MIN). */
+HBV_API int hbv_b200_set_option(const char* name, int64_t value);
+HBV_API int64_t hbv_b200_get_option(const char* name);
+/* launches of the stage-pipelined kernels K1p / K2p (csrc/hbv_pipe.cu; a subset of lean_launches) */
+HBV_API int64_t hbv_b200_pipe_launches(void);
 
 #ifdef __cplusplus
 }

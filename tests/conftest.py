@@ -53,8 +53,77 @@ def maxnorm_err(a, b):
     return num / denom if denom > 0 else num
 
 
-def assert_close(a, b, rtol, what):
+# per-parameter-block gradient check: floor (fraction of the tensor's max-norm) below which a
+# block's error is fp32 accumulation noise — the reference's own fp32 gradient differs from its
+# fp64 evaluation by up to 4e-5 of a block that is 1e-3 of the largest (measured on the golden
+# cases), i.e. ~1e-7 of the tensor's max-norm
+GRAD_BLOCK_FLOOR = 2e-7
+
+
+def assert_grad_close(a, b, what, nmul, rtol=RTOL_GRAD):
+    """Parameter-gradient parity PER PARAMETER BLOCK: the last dimension is cut into runs of `nmul`
+    columns (one physical parameter each; a shorter tail = the routing columns) and every block
+    must satisfy  ||a_blk - b_blk||_inf <= rtol * ||b_blk||_inf + GRAD_BLOCK_FLOOR * ||b||_inf.
+    A single max-norm over the whole tensor would let a block whose gradient is 1000x smaller
+    than the largest (parCFR, parCWH next to parFC) be entirely wrong and still pass."""
     assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
     assert torch.isfinite(a).all(), f'{what}: non-finite values'
-    e = maxnorm_err(a, b)
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    gmax = b.abs().max().item()
+    ncol = a.shape[-1]
+    worst = (0.0, -1)
+    for c0 in range(0, ncol, nmul):
+        ab, bb = a[..., c0:c0 + nmul], b[..., c0:c0 + nmul]
+        nb = bb.abs().max().item()
+        e = (ab - bb).abs().max().item()
+        allowed = rtol * nb + GRAD_BLOCK_FLOOR * gmax
+        assert e <= allowed, (f'{what}: parameter block {c0 // nmul} (columns {c0}..{min(ncol, c0 + nmul) - 1}): '
+                              f'error {e:.3e} > {allowed:.3e} (block max-norm {nb:.3e}, tensor max-norm {gmax:.3e})')
+        if nb > 0 and e / nb > worst[0]:
+            worst = (e / nb, c0 // nmul)
+    return worst
+
+
+# `excs` = max(SM1 - FC, 0) (hbv.py:469-471) is a difference of two O(100) storages: one float32
+# ulp of SM is up to 1e-3 of the excess series' max-norm where little excess occurs, and the
+# reference's own fp32 evaluation differs from its fp64 evaluation by up to 9e-6 of that norm on
+# the golden cases (hbv_2_d3_nowarm; scripts/parity_report.py).  That one series is held to 1e-4
+# against the goldens; the fp64-arbiter gate of SURVEY §8 d6 (err(new, fp64) <= 2 err(ref32, fp64),
+# tests/test_arbiter_gpu.py) is what bounds it tightly.
+RTOL_BY_KEY = {'excs': 1e-4}
+
+
+def flux_rtol(key: str) -> float:
+    return RTOL_BY_KEY.get(key, RTOL_FLUX)
+
+
+# Storages start at 0.001 (hbv.py:133) and the hourly model lifts anything below `nearzero` back
+# at the next step (hbv_2_hourly.py:529-533); an upper-zone storage that empties every step
+# (SUZ = SUZ1 - (SUZ1 / dt) * dt) is pure rounding residue, ~1e-11, whose value depends on whether
+# `/ dt` is a division (ATen on the CPU) or a multiplication by 1/dt (ATen on CUDA, and here).
+# State tensors are therefore compared relative to max(||ref||_inf, STATE_FLOOR).
+STATE_FLOOR = 1e-3
+
+
+def assert_close(a, b, rtol, what, floor=0.0):
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    assert torch.isfinite(a).all(), f'{what}: non-finite values'
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    denom = max(b.abs().max().item(), floor)
+    num = (a - b).abs().max().item()
+    e = num / denom if denom > 0 else num
     assert e <= rtol, f'{what}: max-norm relative error {e:.3e} > {rtol:.1e}'
+
+
+@pytest.fixture(autouse=True)
+def _reset_library_options():
+    """Tests switch kernel families through `_cabi.set_option`; put every switch back to "unset"
+    (the library's own policy) afterwards."""
+    yield
+    if torch.cuda.is_available():
+        from hydrodl2_b200 import _cabi
+        for name in ('lean', 'pipe', 'pipe_max', 'ring', 'lean_small', 'lean_bwd_ring', 'dense',
+                     'dense_ns', 'dense_ns_bwd', 'dense_minb'):
+            _cabi.set_option(name, -1)

@@ -56,6 +56,8 @@ def cotangent(out, seed):
 
 
 def save(name, **arrs):
+    if ONLY and name not in ONLY:
+        return
     flat = {}
     for k, v in arrs.items():
         if isinstance(v, dict):
@@ -90,10 +92,11 @@ def packed_case(hydrodl2, case, model, cls, dyn, T, B, nmul, warm_up, dy_drop, s
          warm_up_states=int(warm_up_states))
 
 
-def split_case(hydrodl2, case, model, cls, dyn, T, B, nmul, dy_drop, seed, routing=False):
+def split_case(hydrodl2, case, model, cls, dyn, T, B, nmul, dy_drop, seed, routing=False, **extra_cfg):
     M = hydrodl2.load_model(model, ver_name=cls)
     cfg = {'dynamic_params': {cls: dyn}, 'nmul': nmul, 'dy_drop': dy_drop,
            'routing': routing}
+    cfg.update(extra_cfg)
     m = M(cfg, device=torch.device('cpu'))
     hourly = model == 'hbv_2_hourly'
     x = synthetic_forcing(T, B, seed=seed, hourly=hourly)
@@ -127,6 +130,7 @@ def split_case(hydrodl2, case, model, cls, dyn, T, B, nmul, dy_drop, seed, routi
          series=dict(zip(m.state_names, m._state_cache)),
          meta=np.array([T, B, nmul, 0, seed + 2]), dy_drop=dy_drop,
          dyn=np.array(dyn, dtype='U16'), model=model, routing=int(routing),
+         warm_up=int(extra_cfg.get('warm_up', 0)), warm_up_states=int(extra_cfg.get('warm_up_states', True)),
          **({'p2': params[2]} if hourly else {}), **extra)
 
 
@@ -167,6 +171,9 @@ def mts_case(hydrodl2, case, T_low, T_high, B, nmul, seed):
          meta=np.array([T_low, T_high, B, nmul, seed + 2]), dyn=np.array(dyn, dtype='U16'))
 
 
+ONLY = set(sys.argv[1:])
+
+
 def main():
     hydrodl2 = import_reference()
     D2 = ['parBETA', 'parBETAET']
@@ -186,6 +193,13 @@ def main():
     split_case(hydrodl2, 'hbv_2_hourly_d3', 'hbv_2_hourly', 'Hbv_2_hourly',
                ['parBETA', 'parK0', 'parBETAET'], 120, 6, 16, 0.0, 700)
     mts_case(hydrodl2, 'hbv_2_mts_train', 40, 96, 6, 4, 800)
+    # round 2: warm_up > 0 with warm_up_states=False on a split model (the 2.0 models never set
+    # `pred_cutoff`, so all T rows come back — hbv_2.py:666-669), and the hourly model's per-unit
+    # gamma-UH routing with lenF = 72 (hbv_2_hourly.py:684-705) under the pair routing
+    split_case(hydrodl2, 'hbv_2_d3_nowarm', 'hbv_2', 'Hbv_2', ['parBETA', 'parK0', 'parBETAET'],
+               48, 5, 16, 0.0, 900, warm_up=8, warm_up_states=False)
+    split_case(hydrodl2, 'hbv_2_hourly_rout72', 'hbv_2_hourly', 'Hbv_2_hourly',
+               ['parBETA', 'parK0', 'parBETAET'], 150, 6, 16, 0.0, 950, routing=True)
 
 
 if __name__ == '__main__':

@@ -10,7 +10,7 @@ from conftest import assert_close, load_golden
 from oracle import hbv_oracle as O
 
 PACKED = ['hbv_static', 'hbv_d2', 'hbv_d2_drop_nowarm', 'hbv_1_1p_d3', 'hbv_1_1p_d14']
-SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3']
+SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3', 'hbv_2_d3_nowarm', 'hbv_2_hourly_rout72']
 TIGHT = 1e-7
 
 

@@ -5,7 +5,8 @@ CPU oracle on seeded inputs.  Tolerances: max-norm relative 1e-5 fluxes/states, 
 import pytest
 import torch
 
-from conftest import RTOL_FLUX, RTOL_GRAD, assert_close, load_golden
+from hydrodl2_b200 import _cabi
+from conftest import RTOL_FLUX, RTOL_GRAD, STATE_FLOOR, assert_close, assert_grad_close, flux_rtol, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -52,7 +53,7 @@ def test_gradient_matches_reference(case, ckpt):
     for k, c in g['cot'].items():
         loss = loss + (out[k] * c.to(dev)).sum()
     loss.backward()
-    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad K={ckpt}')
+    assert_grad_close(p.grad, g['grad_parameters'], f'{case}:grad K={ckpt}', int(g['meta'][2]))
 
 
 @pytest.mark.parametrize('ring', ['0', '1'])
@@ -62,7 +63,7 @@ def test_gradient_both_input_paths(case, ckpt, ring, monkeypatch):
     """The golden cases are small, so by default they take the shared-memory-ring kernels; force
     each input path (HBV_B200_RING: 0 = register prefetch of the throughput regime, incl. its
     every-state-stored sweep at K = 1; 1 = cp.async ring) and check fluxes + gradient on both."""
-    monkeypatch.setenv('HBV_B200_RING', ring)
+    _cabi.set_option('ring', int(ring))
     dev = torch.device('cuda:0')
     g = load_golden(case)
     m, out, p = _run_packed(g, dev, ckpt)
@@ -72,7 +73,7 @@ def test_gradient_both_input_paths(case, ckpt, ring, monkeypatch):
     loss.backward()
     for k, ref in g['out'].items():
         assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k} ring={ring}')
-    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad K={ckpt} ring={ring}')
+    assert_grad_close(p.grad, g['grad_parameters'], f'{case}:grad K={ckpt} ring={ring}', int(g['meta'][2]))
 
 
 def test_streamflow_only_gradient_vs_oracle():
@@ -95,7 +96,7 @@ def test_streamflow_only_gradient_vs_oracle():
     out['streamflow'].sum().backward()
     for k in ref:
         assert_close(out[k], ref[k], RTOL_FLUX, k)
-    assert_close(pg.grad, pc.grad, RTOL_GRAD, 'grad')
+    assert_grad_close(pg.grad, pc.grad, 'grad', nmul)
 
 
 @pytest.mark.parametrize('fused', [True, False])
@@ -116,10 +117,12 @@ def test_fused_zero_fill_gradient(case, fused):
         loss.backward()
     finally:
         ops.FUSED_ZERO_FILL = prev
-    assert_close(p.grad, g['grad_parameters'], RTOL_GRAD, f'{case}:grad fused zero-fill={fused}')
+    assert_grad_close(p.grad, g['grad_parameters'], f'{case}:grad fused zero-fill={fused}', int(g['meta'][2]))
 
 
-SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3']
+# the last two: warm_up > 0 with warm_up_states=False on a split model, and the hourly
+# model's per-unit 72-tap gamma-UH routing under the pair routing (hbv_2_hourly.py:684-705)
+SPLIT = ['hbv_2_d3', 'hbv_2_d3_rout', 'hbv_2_hourly_d3', 'hbv_2_d3_nowarm', 'hbv_2_hourly_rout72']
 SPLIT_CLS = {'hbv_2': 'Hbv_2', 'hbv_2_hourly': 'Hbv_2_hourly'}
 
 
@@ -132,6 +135,8 @@ def _run_split(g, dev, ckpt=16, state_series=True):
     cfg = {'dynamic_params': {cls: [str(s) for s in g['dyn']]}, 'nmul': nmul,
            'dy_drop': float(g['dy_drop']), 'routing': bool(int(g['routing'])),
            'ckpt_interval': ckpt, 'state_series': state_series}
+    if 'warm_up' in g:
+        cfg.update(warm_up=int(g['warm_up']), warm_up_states=bool(int(g['warm_up_states'])))
     m = M(cfg, device=dev)
     p0 = g['p0'].to(dev).requires_grad_(True)
     p1 = g['p1'].to(dev).requires_grad_(True)
@@ -154,9 +159,9 @@ def test_split_forward_matches_reference(case, ckpt):
     m, out, _ = _run_split(g, dev, ckpt)
     assert set(out.keys()) == set(g['out'].keys())
     for k, ref in g['out'].items():
-        assert_close(out[k], ref, RTOL_FLUX, f'{case}:{k}')
+        assert_close(out[k], ref, flux_rtol(k), f'{case}:{k}')
     for name, s in zip(m.state_names, m._state_cache):
-        assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name}')
+        assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name}', floor=STATE_FLOOR)
 
 
 @pytest.mark.parametrize('ckpt,series', [(1, False), (16, True), (0, True), (1, True)])
@@ -169,13 +174,13 @@ def test_split_gradient_matches_reference(case, ckpt, series):
     for k, c in g['cot'].items():
         loss = loss + (out[k] * c.to(dev)).sum()
     loss.backward()
-    assert_close(params[0].grad, g['grad']['p0'], RTOL_GRAD, f'{case}:grad dyn K={ckpt}')
-    assert_close(params[1].grad, g['grad']['p1'], RTOL_GRAD, f'{case}:grad static K={ckpt}')
+    assert_grad_close(params[0].grad, g['grad']['p0'], f'{case}:grad dyn K={ckpt}', int(g['meta'][2]))
+    assert_grad_close(params[1].grad, g['grad']['p1'], f'{case}:grad static K={ckpt}', int(g['meta'][2]))
     if len(params) > 2:
-        assert_close(params[2].grad, g['grad']['p2'], RTOL_GRAD, f'{case}:grad distr K={ckpt}')
+        assert_grad_close(params[2].grad, g['grad']['p2'], f'{case}:grad distr K={ckpt}', 1)
     if series:
         for name, s in zip(m.state_names, m._state_cache):
-            assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name} K={ckpt}')
+            assert_close(s, g['series'][name], RTOL_FLUX, f'{case}:series {name} K={ckpt}', floor=STATE_FLOOR)
 
 
 def test_mts_matches_reference():
