@@ -127,3 +127,45 @@ def _reset_library_options():
         for name in ('lean', 'pipe', 'pipe_max', 'ring', 'lean_small', 'lean_bwd_ring', 'dense',
                      'dense_ns', 'dense_ns_bwd', 'dense_minb'):
             _cabi.set_option(name, -1)
+
+
+def arbiter_gate(new, ref32, ref64, what, slack=1e-6, floor=0.0):
+    """the CUDA result may be no further from the float64 evaluation than twice the
+    reference's own float32 evaluation is:  err(new, fp64) <= 2 err(ref32, fp64) + slack
+    (max-norm, relative to max(||fp64||_inf, floor)).  Returns (err_new, err_ref)."""
+    r64 = ref64.detach().double().cpu()
+    den = max(r64.abs().max().item(), floor)
+    if den == 0:
+        den = 1.0
+    e_new = (new.detach().double().cpu() - r64).abs().max().item() / den
+    e_ref = (ref32.detach().double().cpu() - r64).abs().max().item() / den
+    assert e_new <= 2 * e_ref + slack, (f'{what}: err(new, fp64) = {e_new:.3e} > 2 x err(ref fp32, fp64) = '
+                                       f'{e_ref:.3e} (+ {slack:.0e})')
+    return e_new, e_ref
+
+
+def check_split_slice_vs_oracle(model, x_dict, p0, p1, dyn_names, out, grads, loss_key, what, n=24, nmul=16):
+    """Oracle leg of the kernel-family tests on the hbv_2 family: basins are independent, so the
+    first `n` units of a large-grid CUDA run (loss = out[loss_key].sum(), no routing) must match
+    the CPU oracle run on those units alone — outputs to RTOL_FLUX, the dynamic / static parameter
+    gradients per parameter block — and pass the float64 arbiter gate.  Series listed in
+    RTOL_BY_KEY (cancellation-limited) are held to the gate alone: on these short runs their
+    max-norm can be ~1e-4 mm, where one ulp of the storages they are a difference of is 1e-3 of it
+    and the reference's own fp32 result is that far from fp64."""
+    from oracle import hbv_oracle as O
+    xs = {'x_phy': x_dict['x_phy'][:, :n].detach().cpu(), 'ac_all': x_dict['ac_all'][:n].detach().cpu(),
+          'elev_all': x_dict['elev_all'][:n].detach().cpu()}
+    q0 = p0[:, :n].detach().cpu().clone().requires_grad_(True)
+    q1 = p1[:n].detach().cpu().clone().requires_grad_(True)
+    kw = dict(nmul=nmul, dynamic_params=list(dyn_names), routing=False, use_distr_routing=False)
+    ref, _ = O.forward_split(model, xs, [q0, q1], **kw)
+    ref[loss_key].sum().backward()
+    with torch.no_grad():
+        ref64, _ = O.forward_split(model, xs, [q0.detach(), q1.detach()], dtype=torch.float64, **kw)
+    for k, v in ref.items():
+        if k in out and out[k] is not None and out[k].dim() == 3:
+            if k not in RTOL_BY_KEY:
+                assert_close(out[k][:, :n], v, RTOL_FLUX, f'{what} vs oracle:{k}')
+            arbiter_gate(out[k][:, :n], v, ref64[k], f'{what} arbiter:{k}')
+    assert_grad_close(grads[0][:, :n], q0.grad, f'{what} vs oracle: grad dyn', nmul)
+    assert_grad_close(grads[1][:n], q1.grad, f'{what} vs oracle: grad static', nmul)

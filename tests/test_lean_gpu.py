@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from hydrodl2_b200 import _cabi
-from conftest import RTOL_FLUX, RTOL_GRAD, assert_close, assert_grad_close
+from conftest import RTOL_FLUX, RTOL_GRAD, assert_close, assert_grad_close, check_split_slice_vs_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -148,6 +148,8 @@ def test_lean_hbv_2_matches_k1_k2(B, monkeypatch):
         assert_close(out1[k], out0[k], XTOL, f'hbv_2 lean vs K1 B={B}:{k}')
     for a, b, n in zip(g1, g0, ('dyn', 'static')):
         assert_close(a, b, XTOL, f'hbv_2 lean vs K2 B={B}:grad {n}')
+    # oracle leg (not only transitively through K1 / K2)
+    check_split_slice_vs_oracle('hbv_2', xd, p0, p1, D3, out1, g1, 'streamflow', f'hbv_2 lean B={B}')
 
 
 def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
@@ -173,6 +175,7 @@ def test_lean_hbv_2_hourly_matches_k1_k2(monkeypatch):
     assert_close(out1['Qs'], out0['Qs'], XTOL, 'hourly lean vs K1: Qs')
     for a, b, n in zip(g1, g0, ('dyn', 'static')):
         assert_close(a, b, XTOL, f'hourly lean vs K2: grad {n}')
+    check_split_slice_vs_oracle('hbv_2_hourly', xd, p0, p1, D3, out1, g1, 'Qs', 'hourly lean')
 
 
 def test_lean_fused_zero_fill_on_poisoned_memory(monkeypatch):
