@@ -20,8 +20,11 @@ device-resident measurement on the north-star per-GPU shards, where the kernels 
 rather than latency-bound: "shard" (same model, 22,500 basins) and "c3" (BASELINE configs[2]:
 hbv_1_1p with all 14 parameters dynamic, 22,500 basins x 730 days — the HBM-bound case).
 
-`--impl reference` times the CPU oracle port (the reference is pure Python/PyTorch and is not
-shipped to the GPU box; the port is bit-exact against it, tests/test_oracle_golden.py).
+`--impl reference` times the UNMODIFIED reference (mhpi/hydrodl2's own `Hbv.forward` + autograd,
+installed into the git-ignored baseline/_ref/ by scripts/install_reference.py) on the host cores,
+on the SAME workload: BASELINE configs[1] in full, every step.  Only when baseline/_ref is absent
+does it fall back to the oracle port (bit-exact against the reference, tests/).  `cpu_baseline`
+of the B200 arm is one such step plus BASELINE configs[0] (forward only).
 """
 
 from __future__ import annotations
@@ -56,9 +59,15 @@ WORKLOADS = {
     'c3': dict(model='hbv_1_1p', cls='Hbv_1_1p', dyn=D14, n_par=14, nflux=12, warm_up=0, T=730,
                B=22500, label='c3: hbv_1_1p fwd+bwd, all 14 parameters dynamic, 180k basins / 8 GPUs'),
 }
+# SURVEY.md §8 (d4) worked figures, bytes per basin-timestep (K = 32, one upstream series), quoted
+# literally next to this file's own accounting (which charges the K = 1 state traffic and the
+# dense gradient rows the adjoint writes): {workload: (forward, backward)}
+SURVEY_BYTES = {'c2': (200.0, 292.0), 'shard': (200.0, 292.0), 'c3': (972.0, 1828.0), 'c4': (208.0, 420.0)}
 SEED = 20261017
 # diagnostic only: time the step without the shared-gradient all-reduce
 NO_ALLREDUCE = os.environ.get('HBV_BENCH_NO_ALLREDUCE') == '1'
+# capture the shared-gradient all-reduce inside the CUDA graph of the step (several GPUs)
+GRAPH_ALLREDUCE = os.environ.get('HBV_BENCH_GRAPH_ALLREDUCE', '0') == '1'
 
 
 # ----------------------------------------------------------------------------------------------
@@ -240,21 +249,69 @@ def describe(wl, B):
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on host cores
+# reference arm / CPU baseline: the unmodified reference (baseline/_ref) on the host cores,
+# else the oracle port
 # ----------------------------------------------------------------------------------------------
-def cpu_step(wl, x, p, frac=1.0):
-    """One fwd+bwd of the CPU oracle on the first `frac` of the warm-up and of the run."""
-    from oracle import hbv_oracle as O
-    W, Tm = wl['warm_up'], wl['T']
-    w = max(1, int(round(W * frac))) if W else 0
-    m = max(1, int(round(Tm * frac)))
-    xs = torch.cat([x[:w], x[W:W + m]])
-    ps = torch.cat([p[:w], p[W:W + m]]).detach().requires_grad_(True)
-    t0 = time.perf_counter()
-    out, _ = O.forward_packed(wl['model'], xs, ps, nmul=NMUL, warm_up=w, dynamic_params=wl['dyn'])
-    out['streamflow'].sum().backward()
-    dt = time.perf_counter() - t0
-    return dt, x.shape[1] * m, (w, m)
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def load_reference():
+    """The unmodified reference package from baseline/_ref (scripts/install_reference.py), or None."""
+    if not os.path.isdir(os.path.join(REF_DIR, 'hydrodl2')):
+        return None
+    os.environ.setdefault('CI', '1')          # licence prompt bypass (hydrodl2/__init__.py:103-122)
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import logging
+        logging.getLogger('hydrodl2').setLevel(logging.ERROR)
+        import hydrodl2 as ref
+        return ref
+    except Exception as exc:    # pragma: no cover
+        print(f'bench.py: baseline/_ref present but not importable ({exc}); using the oracle port', file=sys.stderr)
+        return None
+
+
+class CpuArm:
+    """One workload on the host: the reference's own module (kind 'reference') or the oracle port."""
+
+    def __init__(self, wl):
+        self.wl = wl
+        self.ref = load_reference()
+        self.kind = 'reference' if self.ref is not None else 'port'
+        self.model = None
+        if self.ref is not None:
+            M = self.ref.load_model(wl['model'], ver_name=wl['cls'])
+            self.model = M(model_config(wl), device=torch.device('cpu'))
+
+    def train_step(self, x, p):
+        """fwd + bwd of the whole workload (warm-up + run); -> seconds."""
+        wl = self.wl
+        pr = p.detach().clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        if self.model is not None:
+            out = self.model({'x_phy': x}, pr)
+        else:
+            from oracle import hbv_oracle as O
+            out, _ = O.forward_packed(wl['model'], x, pr, nmul=NMUL, warm_up=wl['warm_up'], dynamic_params=wl['dyn'])
+        out['streamflow'].sum().backward()
+        return time.perf_counter() - t0
+
+    def forward_only(self, x, p):
+        """BASELINE configs[0]: forward under no_grad over the run rows only (no warm-up); -> seconds."""
+        wl = self.wl
+        W = wl['warm_up']
+        xs, ps = x[W:].contiguous(), p[W:].contiguous()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.ref is not None:
+                M = self.ref.load_model(wl['model'], ver_name=wl['cls'])
+                m0 = M(dict(model_config(wl), warm_up=0), device=torch.device('cpu'))
+                m0({'x_phy': xs}, ps)
+            else:
+                from oracle import hbv_oracle as O
+                O.forward_packed(wl['model'], xs, ps, nmul=NMUL, warm_up=0, dynamic_params=wl['dyn'])
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -265,31 +322,27 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B = wl['B'] if args.basins is None else args.basins
-    Bs = min(B, 531)   # bounded sample of the workload's basins
-    x, p = make_inputs(wl, Bs, SEED)
-    # size the per-step sample so the whole run stays within a few minutes
-    t_probe, _, _ = cpu_step(wl, x, p, frac=0.05)
-    est_full = t_probe / 0.05
-    budget = 150.0
-    frac = min(1.0, budget / max(1e-9, est_full * (args.steps + args.warmup)))
-    frac = max(frac, 0.02)
+    if B > 531:
+        print('bench.py --impl reference: the CPU arm runs the bench workload (c2) only', file=sys.stderr)
+    x, p = make_inputs(wl, B, SEED)
+    arm = CpuArm(wl)
     for _ in range(args.warmup):
-        cpu_step(wl, x, p, frac)
-    tot, units, wm = 0.0, 0, (0, 0)
+        arm.train_step(x, p)
+    tot = 0.0
     for _ in range(args.steps):
-        dt, u, wm = cpu_step(wl, x, p, frac)
-        tot += dt
-        units += u
-    val = units / tot
-    sample = (f'{Bs} basins x ({wm[0]} warm-up + {wm[1]}) days per step (fraction {frac:.3f} of the '
-              f'{args.workload} time axis), fwd+bwd')
+        tot += arm.train_step(x, p)
+    val = args.steps * B * wl['T'] / tot
+    what = ("unmodified mhpi/hydrodl2 (baseline/_ref): Hbv.forward + autograd" if arm.kind == 'reference'
+            else 'oracle port of the reference (oracle/hbv_oracle.py; baseline/_ref absent)')
+    sample = (f'{what}; every step = the full workload, {B} basins x ({wl["warm_up"]} warm-up + {wl["T"]}) days, '
+              f'fwd+bwd, {cores} threads')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': describe(wl, B), 'sample': sample},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': describe(wl, B)},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': arm.kind, 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -392,10 +445,17 @@ def run_b200(args):
                 traffic = json.load(open(tp)).get(traffic_key, {}).get(kernel)
             except Exception:
                 traffic = None
-        return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'memset + dynamic columns',
-                'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
+        r = {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+             'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+             'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'memset + dynamic columns',
+             'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
+        sb = SURVEY_BYTES.get(traffic_key)
+        if sb and kernel in ('hbv_fwd', 'hbv_bwd'):
+            # SURVEY.md §8 (d4) literal figure (no K = 1 state traffic, gradient = dynamic columns only)
+            lit = sb[0] if kernel == 'hbv_fwd' else sb[1]
+            r['algorithmic_bytes_survey'] = lit
+            r['frac_survey'] = lit * units / (kms[kernel] * 1e-3) / 1e9 / peak
+        return r
 
     # ---------------- the bench workload: device-resident throughput + per-kernel roofline -----
     wl = WORKLOADS[args.workload]
@@ -418,14 +478,23 @@ def run_b200(args):
     if args.graph:
         try:
             from hydrodl2_b200.graphs import GraphedStep
-            # the collective stays outside the graph (capturing NCCL hung on 2 GPUs): each rank
-            # replays its own step, then the shared-gradient all-reduce runs eagerly on the
-            # graph's static output
-            gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
             if world == 1:
+                gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
                 step_fn = gstep.replay
                 graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+            elif GRAPH_ALLREDUCE and not NO_ALLREDUCE:
+                # the shared-gradient all-reduce is captured with the step (thread-local capture mode:
+                # NCCL's watchdog thread may issue CUDA calls while this thread captures)
+                gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=True), warmup=3, device=dev,
+                                    capture_error_mode='thread_local')
+                step_fn = gstep.replay
+                graph_note = ('cuda graph replay of the whole step incl. the NCCL all-reduce of the shared '
+                              'gradient (hydrodl2_b200.graphs.GraphedStep)')
             else:
+                # each rank replays its own step, then the shared-gradient all-reduce runs eagerly on
+                # the graph's static output
+                gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
+
                 def step_fn():
                     _, _, gsh = gstep.replay()
                     if not NO_ALLREDUCE:
@@ -479,18 +548,60 @@ def run_b200(args):
             del model_s, xs, ps
             torch.cuda.empty_cache()
 
+    # BASELINE configs[3] and [4] at their per-GPU sizes (scripts/bench_configs.py): c4 = hbv_2_hourly,
+    # 2,500 units per GPU x 17,520 hourly steps (weak: 20k units on 8 GPUs); c5 = hbv_adj, 10,000 basins
+    # in total, i.e. 10,000 / N per GPU (strong).  Same timing rules (CUDA events, max over ranks).
+    if at_scale is not None and not args.no_configs:
+        import importlib.util
+        spec_ = importlib.util.spec_from_file_location('bench_configs', os.path.join(ROOT, 'scripts', 'bench_configs.py'))
+        cfgs = importlib.util.module_from_spec(spec_)
+        spec_.loader.exec_module(cfgs)
+        for name, fn, kw in (('c4', cfgs.run_c4, {'B': 2500}), ('c5', cfgs.run_c5, {'B': max(1, 10000 // world)})):
+            try:
+                res = fn(3, dev=dev, seed_offset=rank, **kw)
+            except Exception as exc:      # pragma: no cover - keep the bench line alive
+                at_scale[name] = {'error': f'{type(exc).__name__}: {exc}'}
+                torch.cuda.empty_cache()
+                continue
+            ms_max = D.max_over_ranks(res['ms_per_step'], dev)
+            msf_max = D.max_over_ranks(res['fwd_ms_per_step'], dev)
+            units = res['units_per_gpu'] * world
+            entry = {'workload': res['config'], 'value': units / (ms_max * 1e-3), 'unit': UNIT, 'ms_per_step': ms_max,
+                     'fwd_value': units / (msf_max * 1e-3), 'fwd_ms_per_step': msf_max,
+                     'kernel_ms': res['kernel_ms'], 'checks': res['checks'],
+                     'scaling': 'weak' if name == 'c4' else 'strong (10,000 basins in total)'}
+            for leg, kern in (('roofline', res['bwd_kernel']), ('roofline_fwd', res['fwd_kernel'])):
+                by = res['bytes'][kern]
+                ach = by['ours'] * res['units_per_gpu'] / (res['kernel_ms'][kern] * 1e-3) / 1e9
+                entry[leg] = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                              'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                              'algorithmic_bytes_per_basin_step': by['ours'], 'kernel_ms': res['kernel_ms'][kern]}
+                if by.get('survey'):
+                    entry[leg]['algorithmic_bytes_survey'] = by['survey']
+                    entry[leg]['frac_survey'] = by['survey'] * res['units_per_gpu'] / (res['kernel_ms'][kern] * 1e-3) / 1e9 / peak
+            at_scale[name] = entry
+            torch.cuda.empty_cache()
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        Bc = min(B, 531)
-        xc, pc_ = make_inputs(wl, Bc, SEED)
-        frac = 1.0 if B <= 531 else 0.5
-        dt, u, wm = cpu_step(wl, xc, pc_, frac)
-        cpu_baseline = {'value': u / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                        'sample': f'{Bc} basins x ({wm[0]} warm-up + {wm[1]}) days, fwd+bwd, one step, '
-                                  f'{dt:.1f} s of CPU work'}
+        wl_c = WORKLOADS['c2']          # the CPU leg always runs the bench workload at its full size
+        xc, pc_ = make_inputs(wl_c, wl_c['B'], SEED)
+        arm = CpuArm(wl_c)
+        dt = arm.train_step(xc, pc_)
+        dt_f = min(arm.forward_only(xc, pc_) for _ in range(2))
+        what = ('unmodified mhpi/hydrodl2 (baseline/_ref)' if arm.kind == 'reference'
+                else 'oracle port of the reference (baseline/_ref absent)')
+        cpu_baseline = {
+            'value': wl_c['B'] * wl_c['T'] / dt, 'unit': UNIT, 'cores': cores, 'kind': arm.kind,
+            'sample': f"{what}: BASELINE configs[1] in full, {wl_c['B']} basins x ({wl_c['warm_up']} warm-up + "
+                      f"{wl_c['T']}) days, fwd+bwd, one step, {dt:.1f} s of CPU work",
+            'c1_fwd': {'value': wl_c['B'] * wl_c['T'] / dt_f, 'unit': UNIT, 'seconds': dt_f,
+                       'sample': f"BASELINE configs[0]: hbv forward (no_grad), {wl_c['B']} basins x {wl_c['T']} days, "
+                                 f"nmul {NMUL}, best of 2"},
+        }
 
     if rank == 0:
         ncol = wl['n_par'] * NMUL + 2
@@ -550,8 +661,13 @@ def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_ste
         out, loss, _ = train_step(model, inp['x_phy'], inp['parameters'])
         return {'streamflow': out['streamflow'], 'loss': loss, 'grad': inp['parameters'].grad}
 
+    # column-sparse staging: upload only what the kernels read of `parameters` (the dynamic blocks +
+    # the last row + the last warm-up row), download only the non-zero part of its gradient into a
+    # pinned host plane zeroed once — the host still holds the full dense gradient (hostio.py)
     host_in = {'x_phy': x_host, 'parameters': p_host}
-    pipe = PipelinedSteps(pipe_step, host_in, dev, leaf_names=('parameters',))
+    fp = model.io_footprint(p_host.shape[0])
+    pipe = PipelinedSteps(pipe_step, host_in, dev, leaf_names=('parameters',),
+                          in_footprints={'parameters': fp['read']}, out_footprints={'grad': fp['grad']})
 
     def pipe_run(n):
         for _ in range(n):
@@ -569,17 +685,31 @@ def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_ste
     torch.cuda.synchronize(dev)
     D.barrier()
     ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev) / e2e_steps
-    h2d = x_host.numel() * 4 + p_host.numel() * 4
-    d2h = p_host.numel() * 4 + wl['T'] * B * 4 + 4
+    h2d, d2h = int(pipe.h2d_bytes), int(pipe.d2h_bytes)       # counted from the copies the loop issued
+    # the downloaded host plane is the dense gradient: check it against the device tensor once
+    hb = pipe.step(host_in)
+    pipe.drain()
+    p_chk = p_host.to(dev).requires_grad_(True)
+    train_step(model, x_host.to(dev), p_chk)
+    torch.cuda.synchronize(dev)
+    dense_ok = bool(torch.equal(hb['grad'], p_chk.grad.cpu()))
+    del p_chk
     return {'value': world * B * wl['T'] / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'dense_bytes_per_step': {'h2d': x_host.numel() * 4 + p_host.numel() * 4,
+                                     'd2h': p_host.numel() * 4 + wl['T'] * B * 4 + 4},
+            'host_gradient_equals_dense_device_gradient': dense_ok,
             'serial_ms_per_step': ms_serial,
             'pcie_GBps': {'h2d': h2d / (ms_e2e * 1e-3) / 1e9, 'd2h': d2h / (ms_e2e * 1e-3) / 1e9},
             'what': 'pinned host x_phy + parameters -> device, Model.forward + backward, '
                     'streamflow + loss + parameter gradient -> pinned host; double-buffered on '
                     'upload / compute / download streams (hydrodl2_b200.hostio.PipelinedSteps), '
-                    'each step moves its own inputs and results; serial_ms_per_step = the same '
-                    'loop without overlap'}
+                    'each step moves its own inputs and results; column-sparse: of `parameters` only '
+                    'the entries the kernels read (dynamic blocks, last row, last warm-up row) go up, '
+                    'of its gradient only the non-zero entries come down, into a pinned host plane '
+                    'zeroed once (the host holds the full dense gradient: '
+                    'host_gradient_equals_dense_device_gradient); serial_ms_per_step = whole-tensor '
+                    'copies, no overlap (round 1)'}
 
 
 def main():
@@ -594,6 +724,7 @@ def main():
                     help='checkpoint interval of the adjoint (0 = library default: 1 for small problems, else 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 4 and 5 in at_scale')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='time the eager step instead of a CUDA-graph replay of it (single GPU: the step '
                          'is ~0.55 ms of kernels, about what one eager Python step costs the host, so the '

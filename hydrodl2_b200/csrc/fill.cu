@@ -123,3 +123,16 @@ extern "C" int hbv_b200_copy_cols(float* dst, const float* src, int64_t rows, in
     if (e != cudaSuccess) set_error(cudaGetErrorString(e));
     return (int)e;
 }
+
+// DMA-engine alternative to copy_cols (kept for measurement: scripts/experiments/stage_bw.py):
+// cudaMemcpy2DAsync of the same column block; kind 1 = host -> device, 2 = device -> host.
+extern "C" int hbv_b200_memcpy2d(float* dst, const float* src, int64_t rows, int64_t row_stride,
+                                 int32_t col0, int32_t ncols, int32_t kind, void* stream) {
+    using namespace hbv;
+    if (!dst || !src || rows <= 0 || ncols <= 0 || (kind != 1 && kind != 2)) { set_error("memcpy2d: bad arguments"); return HBV_E_SHAPE; }
+    cudaError_t e = cudaMemcpy2DAsync(dst + col0, (size_t)row_stride * 4, src + col0, (size_t)row_stride * 4,
+                                      (size_t)ncols * 4, (size_t)rows,
+                                      kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+    return (int)e;
+}

@@ -29,7 +29,10 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn: Callable[[], Any], warmup: int = 3, device=None):
+    def __init__(self, fn: Callable[[], Any], warmup: int = 3, device=None, capture_error_mode: str = 'global'):
+        """capture_error_mode='thread_local' is what a step containing an NCCL collective needs:
+        NCCL's watchdog thread issues CUDA calls of its own while this thread captures, which the
+        default 'global' mode turns into a capture error."""
         if not torch.cuda.is_available():
             raise RuntimeError('hydrodl2_b200.graphs: CUDA is required (no CPU path)')
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
@@ -42,7 +45,7 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.outputs = fn()
 
     def replay(self):

@@ -22,6 +22,7 @@ PyTorch is used for streams, events and pinned memory only.
 
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, Optional, Sequence
 
 import torch
@@ -35,6 +36,14 @@ def _merge_blocks(blocks):
         else:
             out.append((c0, n))
     return out
+
+
+# How column blocks cross PCIe: 'dma' = cudaMemcpy2DAsync on a copy engine (hbv_b200_memcpy2d),
+# 'kernel' = hbv_b200_copy_cols (the GPU reads / writes the pinned host tensor in place).
+# Measured on B200 at BASELINE config 2's shape (two 64-byte blocks per 840-byte row, 49.6 MB;
+# scripts/experiments/stage_bw.py): dma 1.88 ms up / 2.38 ms down, kernel 2.20 / 2.51 ms, the whole
+# tensor 8.8 ms each way — and the copy engine leaves the SMs to the latency-bound kernels.
+BLOCK_COPY = os.environ.get('HBV_B200_BLOCK_COPY', 'dma')
 
 
 def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cuda.Stream) -> int:
@@ -59,9 +68,14 @@ def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cu
             t1 -= 1
         if t1 > t0:
             off = t0 * B * ncol * 4
+            kind = 1 if dst.is_cuda else 2
             for c0, n in _merge_blocks(fp.get('col_blocks', ())):
-                A.check(lib.hbv_b200_copy_cols(dst.data_ptr() + off, src.data_ptr() + off, (t1 - t0) * B, ncol,
-                                               c0, n, stream.cuda_stream), 'copy_cols')
+                if BLOCK_COPY == 'dma' and dst.is_cuda != src.is_cuda:
+                    A.check(lib.hbv_b200_memcpy2d(dst.data_ptr() + off, src.data_ptr() + off, (t1 - t0) * B, ncol,
+                                                  c0, n, kind, stream.cuda_stream), 'memcpy2d')
+                else:
+                    A.check(lib.hbv_b200_copy_cols(dst.data_ptr() + off, src.data_ptr() + off, (t1 - t0) * B, ncol,
+                                                   c0, n, stream.cuda_stream), 'copy_cols')
                 moved += (t1 - t0) * B * n * 4
     return moved
 

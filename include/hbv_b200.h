@@ -336,6 +336,10 @@ HBV_API int hbv_b200_fill_zero(void* ptr, int64_t nbytes, int32_t n_ctas, void* 
  * hydrodl2_b200.hostio. */
 HBV_API int hbv_b200_copy_cols(float* dst, const float* src, int64_t rows, int64_t row_stride,
                                int32_t col0, int32_t ncols, void* stream);
+/* The same block copy through the DMA engine (cudaMemcpy2DAsync); kind 1 = host -> device,
+ * 2 = device -> host.  Measured against copy_cols in scripts/experiments/stage_bw.py. */
+HBV_API int hbv_b200_memcpy2d(float* dst, const float* src, int64_t rows, int64_t row_stride,
+                              int32_t col0, int32_t ncols, int32_t kind, void* stream);
 /* Experiment / test switches.  Each is read from the environment (HBV_B200_<NAME>) once, when
  * the library is first used, and can be changed at run time here; value -1 = unset (the
  * library's own measured policy decides).  Names (case-insensitive): "lean" (0: never K1s / K2s /

@@ -53,14 +53,14 @@ def timed(fn, steps, warm=2):
     return e0.elapsed_time(e1) / steps
 
 
-def run_c4(steps):
+def run_c4(steps, B=2500, dev=None, seed_offset=0):
     import hydrodl2_b200 as hydrodl2
     from hydrodl2_b200 import ops
-    dev = torch.device('cuda:0')
-    T, B, per_gage = 17520, 2500, 40
+    dev = torch.device('cuda:0') if dev is None else dev
+    T, per_gage = 17520, 40
     dyn = ['parBETA', 'parK0', 'parBETAET']
-    g = torch.Generator(device=dev).manual_seed(4)
-    x = forcing(T, B, dev, 40, hourly=True)
+    g = torch.Generator(device=dev).manual_seed(4 + seed_offset)
+    x = forcing(T, B, dev, 40 + seed_offset, hourly=True)
     p0 = torch.rand(T, B, 3 * NMUL, generator=g, device=dev).requires_grad_(True)
     p1 = torch.rand(B, 16 * NMUL, generator=g, device=dev).requires_grad_(True)
     n_gage = (B + per_gage - 1) // per_gage
@@ -108,7 +108,10 @@ def run_c4(steps):
            device=dev)
     m2.use_distr_routing = False
     # (same mode as the full run — gradients on — so the same kernel instantiation computes both)
-    sub = m2(xs, [p0[:, :64].detach().contiguous().requires_grad_(True), p1[:64].detach().contiguous()])
+    nsub = min(64, B)
+    from hydrodl2_b200 import _cabi
+    with _cabi.option('pipe', 0):      # (the same kernel family as the full grid: K1s / K2s)
+        sub = m2(xs, [p0[:, :nsub].detach().contiguous().requires_grad_(True), p1[:nsub].detach().contiguous()])
     checks['prefix_bit_exact'] = bool(torch.equal(sub['Qs'].detach(), qs[:, :64].detach()))
     n_dyn = 3
     bf = 4 * (3 + n_dyn * NMUL + 1) + 5 * NMUL * 4 / 16
@@ -122,17 +125,22 @@ def run_c4(steps):
         'hbm_GBps_bwd_kernel': bb * B * T / (kms['hbv_bwd'] * 1e-3) / 1e9,
         'algorithmic_bytes_per_basin_step': {'fwd': bf, 'bwd': bb}, 'checks': checks,
         'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9,
+        'units_per_gpu': B * T, 'fwd_kernel': 'hbv_fwd', 'bwd_kernel': 'hbv_bwd',
+        # ours: every state stored (K = 1: 320 B written by the forward, read by the adjoint) and the
+        # gradient's three dynamic blocks written; survey: SURVEY.md §8 (d4) worked figures
+        'bytes': {'hbv_fwd': {'ours': 4.0 * (3 + n_dyn * NMUL + 1) + 320, 'survey': 208.0},
+                  'hbv_bwd': {'ours': 4.0 * (3 + 2 * n_dyn * NMUL + 1) + 320, 'survey': 420.0}},
     }
 
 
-def run_c5(steps):
+def run_c5(steps, B=10000, dev=None, seed_offset=0):
     import hydrodl2_b200 as hydrodl2
     from hydrodl2_b200 import ops
-    dev = torch.device('cuda:0')
-    T, B = 730, 10000
+    dev = torch.device('cuda:0') if dev is None else dev
+    T = 730
     dyn = ['parBETA', 'parBETAET']
-    x = forcing(T, B, dev, 50)
-    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator(device=dev).manual_seed(5),
+    x = forcing(T, B, dev, 50 + seed_offset)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator(device=dev).manual_seed(5 + seed_offset),
                     device=dev).requires_grad_(True)
     M = hydrodl2.load_model('hbv_adj', ver_name='HbvAdj')
     m = M({'warm_up': 0, 'dynamic_params': {'HbvAdj': dyn}, 'nmul': NMUL}, device=dev)
@@ -170,6 +178,11 @@ def run_c5(steps):
         'ms_per_step': ms, 'fwd_ms_per_step': ms_f, 'basin_timesteps_per_s': B * T / (ms * 1e-3),
         'fwd_basin_timesteps_per_s': B * T / (ms_f * 1e-3), 'kernel_ms': kms, 'checks': checks,
         'peak_mem_GB': torch.cuda.max_memory_allocated() / 1e9,
+        'units_per_gpu': B * T, 'fwd_kernel': 'hbv_adj_fwd', 'bwd_kernel': 'hbv_adj_bwd',
+        # forcings + 2 dynamic blocks + Qsim + every converged state; the survey
+        # gives no worked figure for the implicit scheme
+        'bytes': {'hbv_adj_fwd': {'ours': 4.0 * (3 + 32 + 1) + 320, 'survey': None},
+                  'hbv_adj_bwd': {'ours': 4.0 * (3 + 64 + 1) + 320, 'survey': None}},
     }
 
 
