@@ -40,6 +40,7 @@ struct AdjBwdPtrs {
     const float* forcing; const float* dyn; const uint8_t* drop; const float* ysol;
     const float* gqsim; const float* gstate_out;
     float* gdyn; float* gstate_in;
+    int zero_fill;
 };
 
 // Everything one evaluation of the right-hand side produces.
@@ -316,6 +317,21 @@ hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
         float y[5];
 #pragma unroll
         for (int s = 0; s < 5; ++s) y[s] = ynx[s];
+        if (io.zero_fill) {
+            // fused zero fill (nmul 16): a warp owns two basins, whose gradient rows of step t are
+            // one contiguous, 8 B-aligned run; zero it with 8 B stores, then the lanes store their
+            // gradients on top.  Row T-1 also receives the static-parameter and routing gradients.
+            if (t < d.T - 1) {
+                const int wb0 = blockIdx.x * d.BPB + (tid >> 5) * 2;
+                const int nb = min(2, d.B - wb0);
+                if (nb > 0) {
+                    float2* z = reinterpret_cast<float2*>(io.gdyn + ((int64_t)t * d.B + wb0) * d.dyn_ncol);
+                    const int n2 = (nb * d.dyn_ncol) >> 1;
+                    for (int e = tid & 31; e < n2; e += 32) z[e] = make_float2(0.f, 0.f);
+                }
+            }
+            __syncwarp();
+        }
         const float gQ = gqn * inv_nmul * d.dt;
         load_all(t - 1);
         apply_dyn<NPAR, DM>(d, dynmask, cur, p, dpd);
@@ -443,7 +459,14 @@ int adj_bwd_dispatch(const hbv_desc_t* desc, const hbv_adj_bwd_io_t* io, cudaStr
     KDesc d;
     int rc = adj_prepare(desc, d);
     if (rc) return rc;
-    AdjBwdPtrs p{io->forcing, io->dyn, io->drop, io->ysol, io->gqsim, io->gstate_out, io->gdyn, io->gstate_in};
+    AdjBwdPtrs p{io->forcing, io->dyn, io->drop, io->ysol, io->gqsim, io->gstate_out, io->gdyn, io->gstate_in, 0};
+    if (io->gdyn_zero_fill) {
+        if (d.nmul != 16 || d.dyn_ncol % 2 != 0 || reinterpret_cast<uintptr_t>(io->gdyn) % 8 != 0) {
+            set_error("adj_bwd: gdyn_zero_fill needs nmul 16, an even row width and an 8 B-aligned gdyn");
+            return HBV_E_SHAPE;
+        }
+        p.zero_fill = 1;
+    }
     const int dm = static_dynmask(d, io->drop != nullptr);
     if (desc->betaet) {
         if (dm == 0) return launch_adj_bwd<true, 0>(d, p, st);

@@ -121,8 +121,11 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     float F[HBV_MAX_FLUX];
     float gmu_acc = 0.f;
     // per-basin sum of the forcing gradient over the nmul components: shuffles when the lanes of
-    // a basin are an aligned power-of-two group inside a warp, atomics otherwise
+    // a basin are an aligned power-of-two group inside a warp; otherwise through a shared-memory
+    // slab summed in component order by the basin's first lane (deterministic, like every other
+    // reduction in this library — no atomics)
     const bool shfl_reduce = (nmul & (nmul - 1)) == 0 && nmul <= 32 && (NT % 32 == 0 || NT <= 32);
+    float* const fx_slab = smem + d.slack;      // [NT][3] (host: d.slack = offset in floats, 0 = unused)
 
     // One reverse step = (1) `tape_step`: re-evaluate the forward step from its stored state and
     // keep its intermediates, (2) `adj_step`: apply the adjoint.  (1) of step t-1 does not depend
@@ -186,8 +189,18 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
                     gX[2] += __shfl_xor_sync(0xffffffffu, gX[2], o);
                 }
                 if (valid && j == 0) { gx[d.i_prcp] = gX[0]; gx[d.i_tmean] = gX[1]; gx[d.i_pet] = gX[2]; }
-            } else if (valid) {
-                atomicAdd(gx + d.i_prcp, gX[0]); atomicAdd(gx + d.i_tmean, gX[1]); atomicAdd(gx + d.i_pet, gX[2]);
+            } else {
+                // (every thread of the CTA runs the same number of steps: the barriers are uniform)
+                fx_slab[tid * 3 + 0] = gX[0]; fx_slab[tid * 3 + 1] = gX[1]; fx_slab[tid * 3 + 2] = gX[2];
+                __syncthreads();
+                if (valid && j == 0) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                    for (int q = 0; q < nmul; ++q) {
+                        a0 += fx_slab[(tid + q) * 3 + 0]; a1 += fx_slab[(tid + q) * 3 + 1]; a2 += fx_slab[(tid + q) * 3 + 2];
+                    }
+                    gx[d.i_prcp] = a0; gx[d.i_tmean] = a1; gx[d.i_pet] = a2;
+                }
+                __syncthreads();
             }
         }
 
@@ -419,6 +432,9 @@ static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     const int NT = d.BPB * d.nmul;
     const size_t stack = (size_t)d.K * 5 * NT * sizeof(float);
     if (stack > 100 * 1024) { set_error("ckpt_interval * nmul too large for the shared-memory state stack"); return HBV_E_CKPT; }
+    // forcing gradient with nmul not a power of two: a [NT][3] slab after everything else
+    const bool pow2 = (d.nmul & (d.nmul - 1)) == 0 && d.nmul <= 32 && (NT % 32 == 0 || NT <= 32);
+    const size_t fx = (io.gforcing != nullptr && !pow2) ? (size_t)3 * NT * sizeof(float) : 0;
     if constexpr (DM >= 0) {
         constexpr int NSP = (RingSlots<Traits<VAR>::NPAR, DM>::FIRST_FREE + 6) | 1;
         const long long grid = (d.B + d.BPB - 1) / d.BPB;
@@ -426,11 +442,15 @@ static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
         const bool ring = force >= 0 ? (force == 1) : (grid * NT <= 148LL * 4 * 32 * 2);
         if (ring) {
             size_t bytes = 0;
-            d.nstage = choose_nstage(NT, NSP, 1, stack, grid, &bytes);
-            if (d.nstage) return launch_bwd_r<VAR, BETAET, DM, true>(d, io, stack + bytes, st);
+            d.nstage = choose_nstage(NT, NSP, 1, stack + fx, grid, &bytes);
+            if (d.nstage) {
+                d.slack = (int)((stack + bytes) / sizeof(float));
+                return launch_bwd_r<VAR, BETAET, DM, true>(d, io, stack + bytes + fx, st);
+            }
         }
     }
-    return launch_bwd_r<VAR, BETAET, DM, false>(d, io, stack, st);
+    d.slack = (int)(stack / sizeof(float));
+    return launch_bwd_r<VAR, BETAET, DM, false>(d, io, stack + fx, st);
 }
 
 template <int VAR, bool BETAET>

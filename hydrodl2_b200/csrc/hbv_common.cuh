@@ -19,7 +19,8 @@ struct KDesc {
     int muwts_t_stride;
     int BPB;             // basins per CTA
     int nstage;          // input ring: cp.async groups in flight + 1 (2..4); hbv_dense.cu: ring slots
-    int slack;           // hbv_dense.cu: 16 when a staged run may start off a 16 B boundary, else 0
+    int slack;           // hbv_dense.cu: 16 when a staged run may start off a 16 B boundary, else 0;
+                         // hbv_bwd.cu: offset (floats) of the forcing-gradient slab in shared memory
     float nearzero, dt, inv_dt;
     int src[HBV_MAX_PAR];
     int col[HBV_MAX_PAR];

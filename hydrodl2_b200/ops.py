@@ -279,6 +279,11 @@ class _HbvRun(torch.autograd.Function):
         # `track`: grad mode of the caller (inside an autograd.Function it is always off, and a leaf
         # keeps requires_grad=True under no_grad): inference must not pay for stored states
         need_grad = track and any(t is not None and t.requires_grad for t in (dyn, sta, state_in, forcing, muwts))
+        if need_grad and nmul > 128:
+            # the adjoint kernels hold at most 128 lanes per CTA (csrc/hbv_bwd.cu): fail here, before
+            # the forward has run, not in backward()
+            raise RuntimeError(f'hydrodl2_b200: nmul = {nmul} > 128 is supported for inference only '
+                               '(run under torch.no_grad(), or use nmul <= 128 for training)')
         K = spec.ckpt_interval or int(lib.hbv_b200_auto_ckpt(T, B, nmul))   # 0 = auto
         d.ckpt_interval = K
         nseg = (T + K - 1) // K
@@ -589,7 +594,19 @@ class _HbvAdjRun(torch.autograd.Function):
         stream = _stream(dev)
         if ysol is None:
             raise RuntimeError('hydrodl2_b200: backward called but no input required grad')
-        gdyn = torch.zeros_like(dyn)
+        # The dense gradient plane: K3's adjoint zeroes the rows it owns itself (gdyn_zero_fill)
+        # instead of a 6 GB memset in front of it (BASELINE config 5); what it does not own — the
+        # routing columns of the last row of each call's slice — is cleared here.
+        nmul = spec.nmul
+        fused = nmul == 16 and ncol % 2 == 0
+        if fused:
+            gdyn = torch.empty_like(dyn)
+            n_phy = spec.n_par * nmul
+            gdyn[Tt - 1, :, n_phy:].zero_()
+            if warm_up > 0:
+                gdyn[warm_up - 1, :, n_phy:].zero_()
+        else:
+            gdyn = torch.zeros_like(dyn)
 
         def desc_of(sp, nT):
             d = make_desc(sp, nT, B, nvar, ncol, 0)
@@ -620,6 +637,7 @@ class _HbvAdjRun(torch.autograd.Function):
             io.ysol, io.gqsim = _ptr(ysol), _ptr(gq)
             io.gstate_out = None if g_state is None else _ptr(g_state.contiguous())
             io.gdyn, io.gstate_in = _ptr(gdyn[warm_up:]), _ptr(gmid)
+            io.gdyn_zero_fill = int(fused)
             with _timed('hbv_adj_bwd', dev):
                 A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec, T)), C.byref(io), stream), 'adj_bwd')
             gstate_in = gmid
@@ -629,6 +647,7 @@ class _HbvAdjRun(torch.autograd.Function):
                 io.forcing, io.dyn, io.drop = _ptr(forcing), _ptr(dyn), None
                 io.ysol, io.gqsim, io.gstate_out = _ptr(ysol_w), None, _ptr(gmid)
                 io.gdyn, io.gstate_in = _ptr(gdyn), _ptr(gstate_in)
+                io.gdyn_zero_fill = int(fused)
                 with _timed('hbv_adj_bwd_warmup', dev):
                     A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec_w, warm_up)), C.byref(io), stream), 'adj_bwd(warm-up)')
         return (None, None, None, gdyn, gstate_in if state_in.requires_grad else None, None, None, None, None)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HBV_B200_ABI_VERSION 3
+#define HBV_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define HBV_API __attribute__((visibility("default")))
@@ -208,8 +208,13 @@ typedef struct hbv_adj_bwd_io {
     const float* ysol;         /* from the forward call                         */
     const float* gqsim;        /* [T, B] or NULL                                */
     const float* gstate_out;   /* [5, B, nmul] or NULL                          */
-    float* gdyn;               /* [T, B, dyn_ncol], ZERO-INITIALISED by the caller */
+    float* gdyn;               /* [T, B, dyn_ncol]; zero-initialised by the caller unless
+                                  gdyn_zero_fill is set                          */
     float* gstate_in;          /* [5, B, nmul] or NULL                          */
+    int32_t gdyn_zero_fill;    /* 1 (nmul 16, even dyn_ncol only): the kernel zeroes rows 0 .. T-2 of
+                                  gdyn itself before it writes its gradients, so the dense plane needs
+                                  no memset (6 GB at BASELINE config 5); of row T-1 it writes the
+                                  parameter columns only — the caller owns that row's other columns */
 } hbv_adj_bwd_io_t;
 
 HBV_API int hbv_b200_adj_fwd(const hbv_desc_t* desc, const hbv_adj_fwd_io_t* io, void* stream);
@@ -253,7 +258,8 @@ HBV_API int hbv_b200_route_fwd(const hbv_route_desc_t* desc, const float* route,
  *             an all-zero adjoint; its plane is left untouched)
  *   g_route   [B, route_stride]: columns 0,1 written (gradient w.r.t. the raw /
  *             [0,1] routing parameters)
- *   ws        workspace [ (lenF + 2) * nchunk * B ] floats
+ *   ws        workspace [ min(lenF, T) * nchunk * B ] floats (per-tap d/dUH partial sums of the
+ *             nchunk = hbv_b200_route_chunks(T, B) time chunks)
  */
 HBV_API int hbv_b200_route_bwd(const hbv_route_desc_t* desc, const float* route,
                        const float* q_in, int64_t q_stride, const float* q_out,
