@@ -242,6 +242,19 @@ def per_unit_bytes(wl, K, fused=False):
             'route_bwd': 12.0}    # streamflow-only loss: read g, read x, write g_in (1 series)
 
 
+def config_of(wl, B, world):
+    """The `config` object both arms print (identical for the same workload and GPU count)."""
+    ncol = wl['n_par'] * NMUL + 2
+    return {
+        'workload': describe(wl, B),
+        'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
+        'steps_counted': wl['T'], 'nmul': NMUL, 'dynamic_params': list(wl['dyn']),
+        'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
+        'l2': 'inputs larger than L2: parameters + gradient = '
+              f'{2 * (wl["warm_up"] + wl["T"]) * B * ncol * 4 / 1e6:.0f} MB per step vs 126 MB L2',
+    }
+
+
 def describe(wl, B):
     return (f"{wl['label']}, {B} basins/GPU x ({wl['warm_up']} warm-up + {wl['T']}) days, nmul {NMUL}, "
             f"{len(wl['dyn'])} dynamic parameters {wl['dyn'] if len(wl['dyn']) <= 3 else '(all)'}, "
@@ -341,7 +354,7 @@ def run_reference(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': describe(wl, B)},
+        'config': config_of(wl, B, max(1, args.gpus)),
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': arm.kind, 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -368,7 +381,7 @@ def run_b200(args):
         print(f'bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
-    numa = '' if os.environ.get('HBV_BENCH_NO_NUMA') == '1' else D.bind_to_gpu_numa_node(local)
+    numa = 'unchanged (HBV_BENCH_NO_NUMA=1)' if os.environ.get('HBV_BENCH_NO_NUMA') == '1' else D.bind_to_gpu_numa_node(local)
     _cabi.load()
     peak, peak_src = measured_peak_gbs()
 
@@ -604,20 +617,13 @@ def run_b200(args):
         }
 
     if rank == 0:
-        ncol = wl['n_par'] * NMUL + 2
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {
-                'workload': describe(wl, B),
-                'basins_per_gpu': B, 'basins_total': B * world, 'warm_up': wl['warm_up'],
-                'steps_counted': T_MAIN, 'nmul': NMUL, 'ckpt_interval': k_eff(wl, B),
-                'parallelism': f'basin-sharded x{world}, all-reduce of the shared-bias gradient only',
-                'launch': graph_note, 'eager_ms_per_step': ms_eager, 'host_affinity': numa or 'unchanged',
-                'l2': 'inputs larger than L2: parameters + gradient = '
-                      f'{2 * (wl["warm_up"] + T_MAIN) * B * ncol * 4 / 1e6:.0f} MB per step vs 126 MB L2',
-            },
+            'config': config_of(wl, B, world),
+            'run_info': {'ckpt_interval': k_eff(wl, B), 'launch': graph_note, 'eager_ms_per_step': ms_eager,
+                         'host_affinity': numa},
             'clocks': sampler.summary(), 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step,
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'fwd': fwd, 'kernel_ms': kms,

@@ -81,30 +81,46 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
 def bind_to_gpu_numa_node(device_index: int) -> str:
     """Pin this process to the CPUs of the NUMA node its GPU hangs off (from sysfs), so pinned
     host buffers are first-touched in memory local to that GPU's PCIe root — matters for the
-    host <-> device legs when several ranks share a two-socket host.  Best effort: returns a
-    short description of what was done ('' when the topology cannot be read)."""
+    host <-> device legs when several ranks share a two-socket host.  Best effort; always returns
+    a one-line description: what was done, or 'unchanged (<why>)'."""
     try:
         import pynvml as nv
+    except Exception as exc:
+        return f'unchanged (pynvml not importable: {type(exc).__name__})'
+    try:
         nv.nvmlInit()
         vis = os.environ.get('CUDA_VISIBLE_DEVICES')
-        phys = int(vis.split(',')[device_index]) if vis else device_index
+        phys = device_index
+        if vis:
+            tok = vis.split(',')[device_index]
+            if not tok.strip().isdigit():
+                return f'unchanged (CUDA_VISIBLE_DEVICES entry {tok!r} is not an index)'
+            phys = int(tok)
         bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(phys)).busId
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(':')[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
             bus = bus[4:]
         base = f'/sys/bus/pci/devices/{bus}'
+        if not os.path.exists(f'{base}/numa_node'):
+            return f'unchanged ({base}/numa_node not present: no sysfs PCI topology in this container)'
         node = int(open(f'{base}/numa_node').read())
+        if node < 0:
+            return 'unchanged (sysfs reports numa_node = -1: single-node host or virtualised topology)'
         cpus = set()
         for part in open(f'{base}/local_cpulist').read().strip().split(','):
             lo, _, hi = part.partition('-')
             cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if node < 0 or not cpus:
-            return ''
-        os.sched_setaffinity(0, cpus)
-        return f'numa node {node}, {len(cpus)} cpus'
-    except Exception:
-        return ''
+        allowed = os.sched_getaffinity(0)
+        both = cpus & allowed
+        if not both:
+            return (f'unchanged (numa node {node}: none of its {len(cpus)} cpus is in this process\'s '
+                    f'affinity mask of {len(allowed)})')
+        if both == allowed:
+            return f'unchanged (already confined to numa node {node}: {len(allowed)} cpus)'
+        os.sched_setaffinity(0, both)
+        return f'numa node {node}, {len(both)} cpus'
+    except Exception as exc:
+        return f'unchanged ({type(exc).__name__}: {exc})'
 
 
 def allreduce_shared_grad(g: torch.Tensor) -> torch.Tensor:

@@ -13,7 +13,7 @@ import json
 for pipe in (1,0):
     try:
         b=json.load(open(f'gpurun_out/a_bench_c2_pipe{pipe}.json'))
-        print('c2 pipe',pipe,'ms',b['ms_per_step'],'eager',b['config']['eager_ms_per_step'],b['kernel_ms'],'fwd',b['fwd']['kernel_ms'])
+        print('c2 pipe',pipe,'ms',b['ms_per_step'],'eager',b['run_info']['eager_ms_per_step'],b['kernel_ms'],'fwd',b['fwd']['kernel_ms'])
     except Exception as e: print('c2',pipe,e)
     try:
         for ln in open(f'gpurun_out/a_c4_pipe{pipe}.json'):

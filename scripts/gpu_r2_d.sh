@@ -16,6 +16,6 @@ import json
 for tf in (1,0):
     try:
         b=json.load(open(f'gpurun_out/d_bench_c2_tf{tf}.json'))
-        print('c2 thinfill',tf,'ms',b['ms_per_step'],'eager',b['config']['eager_ms_per_step'],b['kernel_ms'])
+        print('c2 thinfill',tf,'ms',b['ms_per_step'],'eager',b['run_info']['eager_ms_per_step'],b['kernel_ms'])
     except Exception as e: print('c2',e)
 PY

@@ -10,7 +10,7 @@ python - <<'PY'
 import json
 try:
     b=json.load(open('gpurun_out/f_bench_c2.json'))
-    print('c2 ms',b['ms_per_step'],'eager',b['config']['eager_ms_per_step'],b['kernel_ms'])
+    print('c2 ms',b['ms_per_step'],'eager',b['run_info']['eager_ms_per_step'],b['kernel_ms'])
 except Exception as e: print('c2',e)
 try:
     for ln in open('gpurun_out/f_c4.json'):

@@ -8,7 +8,7 @@ tail -3 gpurun_out/i_bench.err; cat gpurun_out/i_bench.time
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/i_bench.json'))
-print('c2 ms/step', d['ms_per_step'], 'value %.3e'%d['value'], 'eager', d['config']['eager_ms_per_step'])
+print('c2 ms/step', d['ms_per_step'], 'value %.3e'%d['value'], 'eager', d['run_info']['eager_ms_per_step'])
 print('kernels', {k: round(v,4) for k,v in d['kernel_ms'].items()})
 print('roofline', {k: d['roofline'][k] for k in ('kernel','frac','frac_survey','algorithmic_bytes_per_basin_step','algorithmic_bytes_survey') if k in d['roofline']})
 print('e2e', {k: d['e2e'][k] for k in ('value','ms_per_step','h2d_bytes_per_step','d2h_bytes_per_step','serial_ms_per_step','host_gradient_equals_dense_device_gradient','pcie_GBps')})

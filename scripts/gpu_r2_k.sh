@@ -8,7 +8,7 @@ python - <<PY
 import json
 try:
     d=json.load(open('gpurun_out/k_n2_ga$ga.json'))
-    print('ga=$ga', 'ms', d['ms_per_step'], 'value %.3e'%d['value'], d['config']['launch'][:90], 'e2e', d['e2e']['ms_per_step'] if d['e2e'] else None)
+    print('ga=$ga', 'ms', d['ms_per_step'], 'value %.3e'%d['value'], d['run_info']['launch'][:90], 'e2e', d['e2e']['ms_per_step'] if d['e2e'] else None)
 except Exception as e: print('ga=$ga', e)
 PY
 tail -2 gpurun_out/k_n2_ga$ga.err
