@@ -70,7 +70,10 @@ def _device_inputs(T, B, ncol, dev, seed):
 def test_shard_full_size_properties(name, cls, npar, dyn):
     from oracle import hbv_oracle as O
     dev = torch.device('cuda:0')
-    T, B, nb = 730, 22500, 48
+    # slice of 512 basins (SURVEY §8 d6 asks for 2,048: the CPU oracle's backward takes ~200 s on such
+    # a slice, 512 keeps the suite within the driver's limit; basins are independent, so the slice
+    # size changes the statistics of the comparison, not what is compared)
+    T, B, nb = 730, 22500, 512
     x, p = _device_inputs(T, B, npar * NMUL + 2, dev, seed=5)
     m = _model(name, cls, dyn, 0, dev)
     pg = p.clone().requires_grad_(True)
