@@ -392,7 +392,13 @@ def run_b200(args):
         return model, x, p
 
     def k_eff(wl, B):      # the checkpoint interval the run actually uses (0 = library default)
-        return args.ckpt or int(_cabi.load().hbv_b200_auto_ckpt(wl['T'], B, NMUL))
+        if args.ckpt:
+            return args.ckpt
+        Model = hydrodl2.load_model(wl['model'], ver_name=wl['cls'])
+        spec = Model(model_config(wl), device=dev)._spec(wl['dyn'], True)
+        ncol = wl['n_par'] * NMUL + 2
+        import ctypes
+        return int(_cabi.load().hbv_b200_auto_ckpt_desc(ctypes.byref(ops.make_desc(spec, wl['T'], B, 3, ncol, 0))))
 
     def train_step(model, x_dev, p_dev, allreduce=True):
         p_dev.grad = None
@@ -726,7 +732,7 @@ def main():
     ap.add_argument('--impl', choices=['b200', 'reference'], default='b200')
     ap.add_argument('--workload', choices=list(WORKLOADS), default='c2')
     ap.add_argument('--basins', type=int, default=None, help='override basins per GPU')
-    ap.add_argument('--ckpt', type=int, default=0, choices=[0, 1, 8, 16, 32],
+    ap.add_argument('--ckpt', type=int, default=0, choices=[0, 1, 2, 4, 8, 16, 32],
                     help='checkpoint interval of the adjoint (0 = library default: 1 for small problems, else 16)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')

@@ -16,7 +16,7 @@ static std::atomic<long long> g_pipe_launches{0};
 // option table: environment at first use, then hbv_b200_set_option
 static const char* const kOptNames[OPT_COUNT] = {
     "LEAN", "PIPE", "PIPE_MAX", "RING", "LEAN_SMALL", "LEAN_BWD_RING", "DENSE", "DENSE_NS", "DENSE_NS_BWD",
-    "DENSE_MINB"};
+    "DENSE_MINB", "CKPT"};
 static std::atomic<long long> g_opt[OPT_COUNT];
 static std::atomic<int> g_opt_init{0};
 static void opt_init() {
@@ -140,9 +140,35 @@ int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul) {
     // time-varying parameters, a second read of the parameter tensor that costs more HBM bytes
     // than the states do (measured on B200: hbv_1_1p all-dynamic 22.5k basins, K 16 -> 1:
     // fwd 4.2 -> 4.8 ms, bwd 11.2 -> 7.4 ms).  Longer or wider runs fall back to K = 16.
+    if (hbv::opt(hbv::OPT_CKPT) >= 1) return (int)hbv::opt(hbv::OPT_CKPT);
     const long long lanes = (long long)B * nmul;
     if (lanes * T * 20 <= (16LL << 30)) return 1;
     return 16;
+}
+
+int hbv_b200_auto_ckpt_desc(const hbv_desc_t* desc) {
+    // The interval for one concrete run.  Every state (K = 1) is the default (hbv_b200_auto_ckpt).
+    // Runs the standard-layout kernels serve (nmul 16, 3-wide x_phy, the shipped dynamic sets) have
+    // a second option, the segment sweep of K1s / K2s with K = 4: three of four states are
+    // recomputed in registers instead of travelling through HBM.  Measured on B200 (`hbv`, dynamic
+    // [parBETA, parBETAET], fwd + bwd step, K = 1 / 2 / 4): 531 basins 0.67 / 0.67 / 0.69 ms,
+    // 5,000: 2.19 / 1.96 / 1.86, 10,000: 4.57 / 3.53 / 3.22, 22,500: 8.38 / 7.51 / 6.99 —
+    // so K = 4 from four warps per scheduler up.  The hourly model's adjoint is issue-bound
+    // earlier (2,500 units: 25.1 / 27.8 / 33.0 ms) and keeps K = 1 while the states fit.
+    if (!desc) { hbv::set_error("null descriptor"); return HBV_E_NULL; }
+    const int base = hbv_b200_auto_ckpt(desc->T, desc->B, desc->nmul);
+    if (hbv::opt(hbv::OPT_CKPT) >= 1) return base;
+    if (desc->nmul != 16 || desc->nvar != 3 || hbv::opt(hbv::OPT_LEAN) == 0) return base;
+    int dm = 0;
+    for (int i = 0; i < desc->n_par && i < HBV_MAX_PAR; ++i)
+        if (desc->par_src[i] == HBV_SRC_DYN_T) dm |= 1 << i;
+    const bool packed = desc->variant == HBV_VARIANT_HBV || desc->variant == HBV_VARIANT_HBV11P;
+    const bool lean_set = packed ? (dm == hbv::DM_D2 && desc->betaet) : (dm == hbv::DM_D3);
+    if (!lean_set) return base;
+    const long long lanes = (long long)desc->B * desc->nmul;
+    if (base == 1) return (desc->variant != HBV_VARIANT_HOURLY && lanes >= 148LL * 4 * 32 * 4) ? 4 : 1;
+    // the states of a K = 1 run would not fit 16 GiB: K = 4 while a quarter of them fits 32 GiB
+    return (lanes * desc->T * 20 / 4 <= (32LL << 30)) ? 4 : base;
 }
 
 int64_t hbv_b200_workspace_bytes(const hbv_desc_t* desc) {

@@ -334,6 +334,7 @@ enum Opt {
     OPT_LEAN_BWD_RING,    // 0: K2s register form
     OPT_DENSE,            // 0: never K1d / K2d, 2: wherever the shapes allow (tests), 1 / unset: where they win
     OPT_DENSE_NS, OPT_DENSE_NS_BWD, OPT_DENSE_MINB,
+    OPT_CKPT,             // checkpoint interval hbv_b200_auto_ckpt returns (experiments)
     OPT_COUNT
 };
 long long opt(Opt o);

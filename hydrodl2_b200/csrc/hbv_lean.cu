@@ -72,9 +72,12 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // younger ones too; ncu showed 55-64 % of all stall samples on the first use of a prefetched
 // register)
 // WF: write the flux planes (false: the warm-up / `initialize` run — states only, hbv.py:327-346)
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true>
+// KS: the state before a step is stored every KS-th step (KS = 1, 2 or 4; LTC % KS == 0, so
+// which steps of an output chunk store is known at compile time)
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true, int KS = 1>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
+    static_assert(LTC % KS == 0, "checkpoint interval must divide the output chunk");
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
@@ -140,8 +143,10 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     Tape tp;
     auto do_step = [&](const In& in, int tc) {
         if constexpr (CK) {
+            if (tc % KS == 0) {        // (tc is a literal at every call site)
 #pragma unroll
-            for (int s = 0; s < 5; ++s) { if (valid) *pk = S[s]; pk += nlane; }
+                for (int s = 0; s < 5; ++s) { if (valid) *pk = S[s]; pk += nlane; }
+            }
         }
 #pragma unroll
         for (int i = 0; i < NPAR; ++i)
@@ -276,12 +281,18 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // ZF (one-warp CTAs only): write every element of the gradient rows 0 .. T-2 — the CTA's rows of a
 // step are one contiguous run; the warp zeroes it with 8 B stores, __syncwarp(), then stores the
 // gradients on top — so the dense plane needs no memset (hbv_bwd_io_t.gdyn_zero_fill).
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false>
+// KS (ring form only): the forward stored the state every KS-th step.  The sweep then walks
+// segments of KS steps last-to-first: the segment's inputs (KS ring slots) go to registers, the
+// KS-1 missing states are recomputed from the stored one and kept in registers, and the KS steps
+// are swept in reverse — one extra tape-free forward step per missing state instead of 320 B of
+// state traffic per basin-step written by the forward and read back here.
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false, int KS = 1>
 // (one-warp form: registers unconstrained — 17 resident warps per SM; forcing 20-28 was measured
 // equal or slower on the 22.5k-basin shard, 4.31 / 5.55 / 5.72 ms: the kernel is HBM-bound there)
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
 hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     static_assert(!ZF || LBPB == 2, "fused zero fill needs a one-warp CTA");
+    static_assert(KS == 1 || RD > 0, "the segment sweep is built on the ring form");
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
@@ -378,8 +389,10 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     }
     const int sC = tid >> 3, qC = tid & 7;
     const bool actC = 4 * qC < 16 * nbw;
-    const float* srcC = io.ckpt + ((int64_t)(d.T - 1) * 5 + sC) * nlane + (int64_t)b0w * LNM + 4 * qC;
-    const float* srcD = io.ckpt + ((int64_t)(d.T - 1) * 5 + 4) * nlane + (int64_t)b0w * LNM + 4 * qC;
+    // stored states: plane (segment, state) at ckpt + (5 segment + state) nlane, segment = t / KS
+    const int64_t seg_last = (d.T - 1) / KS;
+    const float* srcC = io.ckpt + (seg_last * 5 + sC) * nlane + (int64_t)b0w * LNM + 4 * qC;
+    const float* srcD = io.ckpt + (seg_last * 5 + 4) * nlane + (int64_t)b0w * LNM + 4 * qC;
     const bool actD = actC && tid < 8;
     const int dstC = STB + sC * 32 + 4 * qC, dstD = STB + 4 * 32 + 4 * qC;
     const int64_t strC = 5 * nlane;
@@ -390,9 +403,12 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
 #pragma unroll
             for (int o = 0; o < NB; ++o)
                 if (actB[o]) cp_async8(wp + dstB[o], srcB[o]);
-            if (actC) cp_async16(wp + dstC, srcC);
-            if (actD) cp_async16(wp + dstD, srcD);
-            srcA -= strA; srcC -= strC; srcD -= strC;
+            if (KS == 1 || t_stage % KS == 0) {      // the state before this step was stored
+                if (actC) cp_async16(wp + dstC, srcC);
+                if (actD) cp_async16(wp + dstD, srcD);
+                srcC -= strC; srcD -= strC;
+            }
+            srcA -= strA;
 #pragma unroll
             for (int o = 0; o < NB; ++o) srcB[o] -= sd;
         }
@@ -437,7 +453,7 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     const int64_t sd2 = sd >> 1;
     int t_cur = d.T - 1;
 
-    auto process = [&](const In& cur) {
+    auto process = [&](const In& cur, const float (&S_in)[5]) {
         if constexpr (ZF) {
             if (t_cur < d.T - 1) {      // row T-1 also holds the static-parameter and routing gradients
 #pragma unroll 4
@@ -454,7 +470,7 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
                 lean_descale_both<SIG>(i, cur.raw[DS::slot(i)], dspan[DS::slot(i)], dlo[DS::slot(i)], p[i], dpd[DS::slot(i)]);
         float S[5];
 #pragma unroll
-        for (int s = 0; s < 5; ++s) S[s] = cur.S[s];
+        for (int s = 0; s < 5; ++s) S[s] = S_in[s];
         float P = cur.P, PET = cur.E;
         if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
         float Fl[HBV_MAX_FLUX];
@@ -477,11 +493,47 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
         }
         pg -= sd;
     };
-    if constexpr (RD > 0) {
+    if constexpr (RD > 0 && KS > 1) {
+        // segment sweep: inputs of the segment's steps in registers (seg[k] = step t0 + k), the
+        // stored state of step t0 arrives with that step's ring slot
+#pragma unroll 1
+        for (int t0 = (int)seg_last * KS; t0 >= 0; t0 -= KS) {
+            const int len = min(KS, d.T - t0);
+            In seg[KS];
+#pragma unroll
+            for (int k = KS - 1; k >= 0; --k)
+                if (k < len) pop(seg[k]);
+            float Sg[KS][5];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) Sg[0][s] = seg[0].S[s];
+#pragma unroll
+            for (int k = 0; k + 1 < KS; ++k) {
+                if (k + 1 < len) {
+#pragma unroll
+                    for (int i = 0; i < NPAR; ++i)
+                        if (DS::is_dyn(i, 0))
+                            p[i] = lean_descale<SIG>(i, seg[k].raw[DS::slot(i)], dspan[DS::slot(i)], dlo[DS::slot(i)]);
+                    float S[5];
+#pragma unroll
+                    for (int s = 0; s < 5; ++s) S[s] = Sg[k][s];
+                    float P = seg[k].P, PET = seg[k].E;
+                    if constexpr (TR::HOURLY) { P = P * d.inv_dt; PET = PET * d.inv_dt; }
+                    float Fl[HBV_MAX_FLUX];
+                    step_fwd<VAR, BETAET, false>(S, p, P, seg[k].T, PET, lc, Fl, tp);
+#pragma unroll
+                    for (int s = 0; s < 5; ++s) Sg[k + 1][s] = S[s];
+                }
+            }
+#pragma unroll
+            for (int k = KS - 1; k >= 0; --k)
+                if (k < len) process(seg[k], Sg[k]);
+        }
+        cp_async_wait<0>();
+    } else if constexpr (RD > 0) {
 #pragma unroll 1
         for (int t = d.T - 1; t >= 0; --t) {
             pop(buf[0]);
-            process(buf[0]);
+            process(buf[0], buf[0].S);
         }
         cp_async_wait<0>();
     } else {
@@ -492,7 +544,7 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
                 if (t - u >= 0) {
                     const In cur = buf[u];
                     load_next(buf[u]);
-                    process(cur);
+                    process(cur, cur.S);
                 }
             }
         }
@@ -568,8 +620,10 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     d.BPB = LBPB;
     const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)RD * (8 + 32 * ND)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    if (io.ckpt != nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    if (io.ckpt == nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else if (d.K == 1) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else if (d.K == 2) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 2><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 4><<<grid, LBPB * LNM, smem, st>>>(d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -613,10 +667,17 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     const size_t smem = (size_t)RD * (8 + 32 * (ND + 5)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
     if constexpr (LBPB == 2) {
-        if (io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol)
-            hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
-        else
-            hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+        const bool zf = io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol;
+        if (d.K == 1) {
+            if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
+            else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
+        } else if (d.K == 2) {
+            if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true, 2><<<grid, LBPB * LNM, smem, st>>>(d, io);
+            else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false, 2><<<grid, LBPB * LNM, smem, st>>>(d, io);
+        } else {
+            if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true, 4><<<grid, LBPB * LNM, smem, st>>>(d, io);
+            else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false, 4><<<grid, LBPB * LNM, smem, st>>>(d, io);
+        }
     } else {
         hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
     }
@@ -639,7 +700,7 @@ int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_
     constexpr int NPAR = Traits<VAR>::NPAR;
     if (!write_flux || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
     if (io.drop != nullptr || io.muwts != nullptr || io.state_series != nullptr) return HBV_NOT_ELIGIBLE;
-    if (io.ckpt != nullptr && d.K != 1) return HBV_NOT_ELIGIBLE;
+    if (io.ckpt != nullptr && d.K != 1 && d.K != 2 && d.K != 4) return HBV_NOT_ELIGIBLE;
     // the ring form copies the parameter runs 8 B at a time
     if (lean_small_grid(d, io.ckpt != nullptr) && (d.dyn_ncol % 2 != 0 || reinterpret_cast<uintptr_t>(io.dyn) % 8 != 0)) return HBV_NOT_ELIGIBLE;
     for (int f = 0; f < Traits<VAR>::NFLUX; ++f)
@@ -655,9 +716,12 @@ int try_fwd_lean(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_
 template <int VAR, bool BETAET, int DM>
 int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     constexpr int NPAR = Traits<VAR>::NPAR;
-    if (d.K != 1 || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
+    if ((d.K != 1 && d.K != 2 && d.K != 4) || !lean_common_ok(d)) return HBV_NOT_ELIGIBLE;
     if (io.drop != nullptr || io.muwts != nullptr || io.gmuwts != nullptr || io.gforcing != nullptr ||
         io.gstate_series != nullptr || io.gdyn == nullptr) return HBV_NOT_ELIGIBLE;
+    // K = 2, 4: the segment sweep exists in the ring form only
+    if (d.K != 1 && !(lean_bwd_ring(d) && reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0 &&
+                      reinterpret_cast<uintptr_t>(io.ckpt) % 16 == 0)) return HBV_NOT_ELIGIBLE;
     // the caller asked for every element to be written (gdyn_zero_fill): nothing to do when every
     // column of `dyn` is a time-varying parameter (split form); otherwise the one-warp form zeroes
     // its rows itself (even row width: 8 B stores)

@@ -284,7 +284,13 @@ class _HbvRun(torch.autograd.Function):
             # the forward has run, not in backward()
             raise RuntimeError(f'hydrodl2_b200: nmul = {nmul} > 128 is supported for inference only '
                                '(run under torch.no_grad(), or use nmul <= 128 for training)')
-        K = spec.ckpt_interval or int(lib.hbv_b200_auto_ckpt(T, B, nmul))   # 0 = auto
+        if spec.ckpt_interval:
+            K = spec.ckpt_interval
+        elif spec.state_series:
+            # the per-step state series rides on the K = 1 store (see below): keep every state
+            K = int(lib.hbv_b200_auto_ckpt(T, B, nmul))
+        else:
+            K = int(lib.hbv_b200_auto_ckpt_desc(C.byref(d)))      # 0 = auto
         d.ckpt_interval = K
         nseg = (T + K - 1) // K
         # `hbv_2` family: the per-step state series (hbv_2.py:571-575, the state AFTER every step)

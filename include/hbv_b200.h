@@ -319,6 +319,10 @@ HBV_API int hbv_b200_auto_ckpt(int32_t T, int32_t B, int32_t nmul);
  * this problem: ceil(T / K) * 5 * B * nmul floats with K = desc->ckpt_interval, or
  * hbv_b200_auto_ckpt(T, B, nmul) when that is 0 (hbv_workspace_bytes).
  * Returns < 0 (HBV_E_*) on a bad descriptor.  The library itself never allocates. */
+/* The checkpoint interval the library would pick for this run (descriptor-aware form of
+ * hbv_b200_auto_ckpt: runs served by the standard-layout kernels use K = 4 on large grids —
+ * measured crossover in csrc/hbv_cabi.cu).  desc->ckpt_interval is ignored. */
+HBV_API int hbv_b200_auto_ckpt_desc(const hbv_desc_t* desc);
 HBV_API int64_t hbv_b200_workspace_bytes(const hbv_desc_t* desc);
 /* number of kernels this library has launched in this process (bench accounting) */
 HBV_API int64_t hbv_b200_launch_count(void);
@@ -352,7 +356,7 @@ HBV_API int hbv_b200_memcpy2d(float* dst, const float* src, int64_t rows, int64_
  * K1p / K2p), "pipe" (0: never K1p / K2p), "pipe_max" (largest grid in lanes for K1p / K2p),
  * "ring" (0 / 1: force register / cp.async-ring inputs in K1 / K2), "lean_small",
  * "lean_bwd_ring", "dense" (0: never K1d / K2d, 2: wherever the shapes allow), "dense_ns",
- * "dense_ns_bwd", "dense_minb".  Returns 0, or HBV_E_SHAPE for an unknown name
+ * "dense_ns_bwd", "dense_minb", "ckpt" (the interval hbv_b200_auto_ckpt returns).  Returns 0, or HBV_E_SHAPE for an unknown name
  * (get: INT64_MIN). */
 HBV_API int hbv_b200_set_option(const char* name, int64_t value);
 HBV_API int64_t hbv_b200_get_option(const char* name);

@@ -8,6 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 from conftest import load_golden, maxnorm_err  # noqa: E402
 import test_parity_gpu as T  # noqa: E402
 
@@ -42,7 +43,50 @@ def main():
         worst['grad'] = max(worst['grad'], eg)
         print(f'{case:22s} flux {ef:.2e} ({kf})  state {es:.2e}  grad {eg:.2e}')
     print('worst', {k: f'{v:.2e}' for k, v in worst.items()}, ' tolerances: flux/state 1e-5, grad 1e-4')
+    per_block(dev)
     full_size(dev)
+    long_hourly(dev)
+
+
+def per_block(dev):
+    """Worst per-parameter-block gradient error (conftest.assert_grad_close) over the golden cases."""
+    from conftest import assert_grad_close
+    print('-- parameter gradients per parameter block (runs of nmul columns): worst relative error, block')
+    for case in T.PACKED:
+        g = load_golden(case)
+        m, out, p = T._run_packed(g, dev)
+        sum((out[k] * c.to(dev)).sum() for k, c in g['cot'].items()).backward()
+        w = assert_grad_close(p.grad, g['grad_parameters'], case, int(g['meta'][2]))
+        print(f'{case:22s} worst block {w[1]:2d}: {w[0]:.2e}')
+    for case in T.SPLIT:
+        g = load_golden(case)
+        m, out, params = T._run_split(g, dev)
+        sum((out[k] * c.to(dev)).sum() for k, c in g['cot'].items()).backward()
+        ws = [assert_grad_close(q.grad, g['grad'][f'p{i}'], case, int(g['meta'][2]) if i < 2 else 1) for i, q in enumerate(params)]
+        print(f'{case:22s} ' + '  '.join(f'p{i}: block {w[1]} {w[0]:.2e}' for i, w in enumerate(ws)))
+
+
+def long_hourly(dev):
+    """BASELINE config 4 at 17,520 steps (tests/test_long_hourly_gpu.py): margins against the fp32
+    oracle and the float64 arbiter for every kernel family."""
+    import test_long_hourly_gpu as L
+    import numpy as np
+    import make_long_hourly as G
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'hbv_2_hourly_long.npz'))
+    ref = {k: torch.from_numpy(z[k]) for k in z.files if k != 'meta'}
+    fx = (G, ref) + tuple(G.inputs())
+    print('-- hbv_2_hourly, 17,520 hourly steps, fwd + bwd: max-norm relative error vs the fp32 oracle | vs float64 '
+          '(oracle fp32 vs float64 in brackets)')
+    e = lambda a, b: maxnorm_err(a.double(), b.double())   # noqa: E731
+    print(f"   oracle fp32 vs float64: Qs {e(ref['Qs32'], ref['Qs64']):.2e}  grad static {e(ref['gsta32'], ref['gsta64']):.2e}  "
+          f"grad dynamic {e(ref['gdyn32'], ref['gdyn64']):.2e}")
+    for n_units, ckpt, lean, what in L.CASES:
+        qs, S, gsta, gdyn, fam = L._run(fx, n_units, ckpt, lean)
+        print(f"   {what:62s} Qs {e(qs, ref['Qs32']):.2e} | {e(qs, ref['Qs64']):.2e}   grad static {e(gsta, ref['gsta32']):.2e} | "
+              f"{e(gsta, ref['gsta64']):.2e}   grad dynamic {e(gdyn, ref['gdyn32']):.2e} | {e(gdyn, ref['gdyn64']):.2e}   "
+              f"launches (lean, pipe) {fam}")
+    from hydrodl2_b200 import _cabi
+    _cabi.set_option('lean', -1)
 
 
 def full_size(dev):
@@ -78,8 +122,8 @@ def full_size(dev):
               f'flux {ef:.2e}  state {es:.2e}  grad {eg:.2e}')
 
     run('hbv', 'Hbv', 13, D2, 1095, 531, 365, 0, 531, 20261017)
-    run('hbv', 'Hbv', 13, D2, 730, 22500, 0, 11111, 48, 5)
-    run('hbv_1_1p', 'Hbv_1_1p', 14, D14, 730, 22500, 0, 11111, 48, 5)
+    run('hbv', 'Hbv', 13, D2, 730, 22500, 0, 11111, 128, 5)
+    run('hbv_1_1p', 'Hbv_1_1p', 14, D14, 730, 22500, 0, 11111, 128, 5)
 
 
 if __name__ == '__main__':

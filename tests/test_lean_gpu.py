@@ -29,11 +29,11 @@ def _lean_count():
     return _cabi.load().hbv_b200_lean_launches()
 
 
-def _run_packed(model, cls, npar, x, p, dev, lean, monkeypatch, warm_up):
+def _run_packed(model, cls, npar, x, p, dev, lean, monkeypatch, warm_up, ckpt=0):
     import hydrodl2_b200 as hydrodl2
     _cabi.set_option('lean', int('1' if lean else '0'))
     M = hydrodl2.load_model(model, ver_name=cls)
-    m = M({'warm_up': warm_up, 'dynamic_params': {cls: D2}, 'nmul': NMUL}, device=dev)
+    m = M({'warm_up': warm_up, 'dynamic_params': {cls: D2}, 'nmul': NMUL, 'ckpt_interval': ckpt}, device=dev)
     pg = p.to(dev).requires_grad_(True)
     out = m({'x_phy': x.to(dev)}, pg)
     out['streamflow'].sum().backward()
@@ -68,6 +68,31 @@ def test_lean_packed_vs_oracle(model, cls, npar, B, monkeypatch):
     for k in ref:
         assert_close(out[k], out0[k], XTOL, f'lean vs K1 {model} B={B}:{k}')
     assert_close(grad, grad0, XTOL, f'lean vs K2 {model} B={B}:grad')
+
+
+@pytest.mark.parametrize('B', [47, 2501])                 # small grid (ring forward) and large (register forward)
+@pytest.mark.parametrize('ckpt', [2, 4])
+def test_lean_segment_sweep_vs_oracle(ckpt, B, monkeypatch):
+    """K1s / K2s with a state stored every 2nd / 4th step (the segment sweep recomputes the missing
+    ones): same results as the oracle, partial last segment included (35 run steps)."""
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, warm = 41, 6
+    nb = min(B, 64)
+    x = O.synthetic_forcing(T, B, seed=43)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(44))
+    pc = p[:, :nb].clone().requires_grad_(True)
+    ref, ref_states = O.forward_packed('hbv', x[:, :nb], pc, nmul=NMUL, warm_up=warm, dynamic_params=D2)
+    ref['streamflow'].sum().backward()
+    n0 = _lean_count()
+    out, grad, m = _run_packed('hbv', 'Hbv', 13, x, p, dev, True, monkeypatch, warm, ckpt=ckpt)
+    assert _lean_count() - n0 == 3, f'K = {ckpt}: warm-up K1s + K1s + K2s should have run'
+    for k, v in ref.items():
+        got = out[k][:nb] if k == 'BFI' else out[k][:, :nb]
+        assert_close(got, v, RTOL_FLUX, f'lean K={ckpt} B={B}:{k}')
+    assert_grad_close(grad[:, :nb], pc.grad, f'lean K={ckpt} B={B}:grad', NMUL)
+    out1, grad1, _ = _run_packed('hbv', 'Hbv', 13, x, p, dev, True, monkeypatch, warm, ckpt=1)
+    assert_close(grad, grad1, XTOL, f'lean K={ckpt} vs K=1 B={B}:grad')
 
 
 def test_lean_forward_only_no_grad(monkeypatch):
