@@ -32,6 +32,8 @@ KEYS = [
     ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue slots busy %'),
     ('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'FMA pipe active %'),
     ('sm__inst_executed_pipe_xu.sum', 'XU (SFU) instructions'),
+    ('smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio', 'stall dispatch / issue'),
+    ('smsp__warps_eligible.avg.per_cycle_active', 'eligible warps per scheduler cycle'),
     ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'stall long_scoreboard / issue'),
     ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'stall short_scoreboard / issue'),
     ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'stall wait / issue'),
@@ -70,7 +72,10 @@ def launches(src, dst):
 
 
 def full(src, dst, workload=None):
-    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if src.endswith('.csv'):       # `ncu -i x.ncu-rep --page raw --csv` already run on the GPU box
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     traffic = {}
@@ -96,6 +101,8 @@ def full(src, dst, workload=None):
                     base = 'hbv_fwd_warmup'
                 if base == 'hbv_fwd_lean_kernel' and len(targs) >= 9 and targs[8] == '0':
                     base = 'hbv_fwd_warmup'
+                if base == 'hbv_fwd_pipe_kernel' and len(targs) >= 7 and targs[6] == '0':
+                    base = 'hbv_fwd_warmup'
                 traffic.setdefault(base, t)
                 f.write(f'| **DRAM traffic per launch** | {t / 1e9:.3f} GB |\n')
             except Exception:
@@ -106,7 +113,8 @@ def full(src, dst, workload=None):
         cur = json.load(open(tp)) if os.path.exists(tp) else {}
         short = {'hbv_fwd_kernel': 'hbv_fwd', 'hbv_bwd_kernel': 'hbv_bwd',
                  'hbv_fwd_lean_kernel': 'hbv_fwd', 'hbv_bwd_lean_kernel': 'hbv_bwd',
-                 'hbv_fwd_dense_kernel': 'hbv_fwd', 'hbv_bwd_dense_kernel': 'hbv_bwd'}
+                 'hbv_fwd_dense_kernel': 'hbv_fwd', 'hbv_bwd_dense_kernel': 'hbv_bwd',
+                 'hbv_fwd_pipe_kernel': 'hbv_fwd', 'hbv_bwd_pipe_kernel': 'hbv_bwd'}
         cur[workload] = {}        # one capture = one consistent set of kernels
         for k, v in traffic.items():
             cur[workload][short.get(k, k)] = v

@@ -80,7 +80,9 @@ def assert_grad_close(a, b, what, nmul, rtol=RTOL_GRAD):
         allowed = rtol * nb + GRAD_BLOCK_FLOOR * gmax
         assert e <= allowed, (f'{what}: parameter block {c0 // nmul} (columns {c0}..{min(ncol, c0 + nmul) - 1}): '
                               f'error {e:.3e} > {allowed:.3e} (block max-norm {nb:.3e}, tensor max-norm {gmax:.3e})')
-        if nb > 0 and e / nb > worst[0]:
+        # (reported: the worst block among those whose tolerance is the relative term, i.e. whose
+        # max-norm is above GRAD_BLOCK_FLOOR / rtol = 2e-3 of the tensor's)
+        if nb * rtol >= GRAD_BLOCK_FLOOR * gmax and e / nb > worst[0]:
             worst = (e / nb, c0 // nmul)
     return worst
 
