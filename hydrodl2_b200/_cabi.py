@@ -51,7 +51,7 @@ class HbvBwdIO(C.Structure):
         ('forcing', _fp), ('dyn', _fp), ('sta', _fp), ('drop', _fp), ('attrs', _fp),
         ('muwts', _fp), ('ckpt', _fp), ('gflux', _fp * HBV_MAX_FLUX), ('gstate_out', _fp),
         ('gstate_series', _fp), ('gdyn', _fp), ('gsta', _fp), ('gstate_in', _fp),
-        ('gdyn_zero_fill', C.c_int32), ('reserved_', C.c_int32), ('gforcing', _fp), ('gmuwts', _fp),
+        ('gdyn_zero_fill', C.c_int32), ('gdyn_rows_before', C.c_int32), ('gforcing', _fp), ('gmuwts', _fp),
     ]
 
 

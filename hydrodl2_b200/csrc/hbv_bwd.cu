@@ -453,17 +453,32 @@ static int launch_bwd_dm(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     return launch_bwd_r<VAR, BETAET, DM, false>(d, io, stack + fx, st);
 }
 
+// the warm-up rows in front of gdyn: only K2p zeroes them itself; every other kernel gets them
+// cleared by a memset in stream order, and is told there is nothing in front
+static int clear_rows_before(const KDesc& d, BwdPtrs& io, cudaStream_t st) {
+    if (io.rows_before <= 0) return 0;
+    const size_t n = (size_t)io.rows_before * d.B * d.dyn_ncol;
+    cudaError_t e = cudaMemsetAsync(io.gdyn - n, 0, n * sizeof(float), st);
+    io.rows_before = 0;
+    if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+    return (int)e;
+}
+
 template <int VAR, bool BETAET>
-static int launch_bwd(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
+static int launch_bwd(const KDesc& d, const BwdPtrs& io_in, cudaStream_t st) {
+    BwdPtrs io = io_in;
     const int dm = static_dynmask(d, io.drop != nullptr);
-    if (dm == 0) return launch_bwd_dm<VAR, BETAET, 0>(d, io, st);
+    if (dm == 0) { if (int rc = clear_rows_before(d, io, st)) return rc; return launch_bwd_dm<VAR, BETAET, 0>(d, io, st); }
     if constexpr (BETAET && (VAR == HBV_VARIANT_HBV || VAR == HBV_VARIANT_HBV11P)) {
         if (dm == DM_D2) {
             int rc = try_bwd_pipe<VAR, BETAET, DM_D2>(d, io, st);                    // hbv_pipe.cu
-            if (rc == HBV_NOT_ELIGIBLE) rc = try_bwd_lean<VAR, BETAET, DM_D2>(d, io, st);   // hbv_lean.cu
+            if (rc != HBV_NOT_ELIGIBLE) return rc;
+            if ((rc = clear_rows_before(d, io, st)) != 0) return rc;
+            rc = try_bwd_lean<VAR, BETAET, DM_D2>(d, io, st);                        // hbv_lean.cu
             return rc != HBV_NOT_ELIGIBLE ? rc : launch_bwd_dm<VAR, BETAET, DM_D2>(d, io, st);
         }
     }
+    if (int rc0 = clear_rows_before(d, io, st)) return rc0;
     if constexpr (VAR == HBV_VARIANT_HBV11P) {
         if (dm == DM_ALL14) {
             const int rc = try_bwd_dense<VAR, BETAET, DM_ALL14>(d, io, st);          // hbv_dense.cu
@@ -498,6 +513,8 @@ int bwd_dispatch(const hbv_desc_t* desc, const hbv_bwd_io_t* io, cudaStream_t st
     p.gforcing = io->gforcing; p.gmuwts = io->muwts ? io->gmuwts : nullptr;
     p.zero_fill = io->gdyn_zero_fill && io->gdyn != nullptr && ((d.BPB * d.dyn_ncol + d.BPB * d.nmul - 1) / (d.BPB * d.nmul) <= 32);
     if (io->gdyn_zero_fill && !p.zero_fill) { set_error("gdyn_zero_fill unsupported for this shape (ncol/nmul > 32)"); return HBV_E_SHAPE; }
+    p.rows_before = (p.zero_fill && io->gdyn_rows_before > 0) ? io->gdyn_rows_before : 0;
+    if (io->gdyn_rows_before > 0 && !p.zero_fill) { set_error("gdyn_rows_before needs gdyn_zero_fill"); return HBV_E_SHAPE; }
     for (int f = 0; f < HBV_MAX_FLUX; ++f) p.gflux[f] = io->gflux[f];
     switch (desc->variant) {
         case HBV_VARIANT_HBV:

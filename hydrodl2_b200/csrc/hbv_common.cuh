@@ -40,6 +40,7 @@ struct BwdPtrs {
     const float* gflux[HBV_MAX_FLUX]; const float* gstate_out; const float* gstate_series;
     float* gdyn; float* gsta; float* gstate_in; float* gforcing; float* gmuwts;
     int zero_fill;
+    int rows_before;     // rows in front of gdyn the adjoint zeroes as well (K2p only; else memset by the dispatcher)
 };
 
 // value in [0,1] (or raw) -> physical parameter

@@ -47,12 +47,16 @@ def _fused_zero_fill(spec, dyn_ncol, n_basins) -> bool:
     n_dyn = sum(1 for s in spec.par_src[:spec.n_par] if s == A.SRC_DYN_T)
     if 2 * n_dyn * spec.nmul >= dyn_ncol:
         return True
-    # nmul 16, even row width: the one-warp adjoint (K2s) zeroes a step's rows with a handful of
-    # 8 B stores before it writes the gradients — cheaper than a memset that competes with the
-    # forward kernels for HBM (22.5k-basin shard) or for the schedulers (531 basins)
-    # (measured: shard step 10.7 -> 9.4 ms; on the 531-basin grid the extra stores sit in the
-    # single warp's critical path and cost more than the in-order memset, 0.57 vs 0.56 ms)
-    return spec.nmul == 16 and dyn_ncol % 2 == 0 and n_basins * spec.nmul > _SMALL_GRID_LANES
+    # nmul 16, even row width: the one-warp adjoint zeroes a step's rows itself before it writes the
+    # gradients — K2s with a handful of 8 B stores (22.5k-basin shard: step 10.7 -> 9.4 ms against
+    # a memset that competes with the forward kernels for HBM).  On small, latency-bound grids the
+    # in-order memset is cheaper: plain stores sit in the single warp's critical path (K2s: 0.57 vs
+    # 0.56 ms), and K2p's variant — ONE TMA bulk store per row from a zeroed shared-memory buffer,
+    # warm-up rows included (gdyn_rows_before; HBV_B200_BULK_ZERO=1) — was measured slower too.
+    if spec.nmul != 16 or dyn_ncol % 2 != 0:
+        return False
+    lanes = n_basins * spec.nmul
+    return lanes > _SMALL_GRID_LANES or (BULK_ZERO_FILL and lanes <= _PIPE_LANES)
 
 # small grids: zero the gradient plane with the library's thin fill kernel on the side stream
 # instead of a memset in stream order.  Off by default — measured on B200 (C2): even a fill that
@@ -61,6 +65,12 @@ def _fused_zero_fill(spec, dyn_ncol, n_basins) -> bool:
 THIN_FILL = os.environ.get('HBV_B200_THIN_FILL', '0') == '1'
 _SIDE_STREAMS = {}
 _SMALL_GRID_LANES = 148 * 4 * 32 * 2      # same boundary as the kernels' small-grid regime
+_PIPE_LANES = 148 * 4 * 32                # K1p / K2p regime (csrc/hbv_pipe.cu: one warp per scheduler)
+# Off by default: measured on B200 (C2) the zeros written from inside K2p — one TMA bulk store per
+# row, 4 or 16 iterations ahead of the gradient stores — slow the sweep from 171 to 326 us (the
+# step 0.465 -> 0.549 ms): 489 MB of extra write traffic next to a latency-bound kernel costs
+# more than the 76 us in-order memset it replaces.
+BULK_ZERO_FILL = os.environ.get('HBV_B200_BULK_ZERO', '0') == '1'
 
 
 def _side_stream(dev):
@@ -214,6 +224,8 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0,
     fused = _fused_zero_fill(spec, dyn.shape[-1], dyn.shape[1])
     if fused and t_off == 0:
         return None           # only the routing columns of one row: the backward clears them in order
+    if fused and dyn.shape[1] * spec.nmul <= _PIPE_LANES:
+        return None           # K2p zeroes the warm-up rows itself (gdyn_rows_before, see backward)
     dev = dyn.device
     gbuf = torch.empty_like(dyn)
 
@@ -402,6 +414,7 @@ class _HbvRun(torch.autograd.Function):
         # gradient, hbv.py:328) and the non-parameter columns of the last row are zeroed here.
         gdyn_full = gdyn_run = None
         zero_fill = 0
+        rows_before = 0
         if dyn is not None:
             if ctx.gbuf is not None:
                 gdyn_full, ctx.gbuf = ctx.gbuf, None
@@ -412,7 +425,10 @@ class _HbvRun(torch.autograd.Function):
                 zero_fill = 1
                 gdyn_full = torch.empty_like(dyn)
                 if t_off > 0:
-                    gdyn_full[:t_off].zero_()
+                    if B * nmul <= _PIPE_LANES:
+                        rows_before = t_off       # zeroed by the call (K2p: bulk stores; else a memset in the library)
+                    else:
+                        gdyn_full[:t_off].zero_()
                 if spec.n_par * nmul < dyn_ncol:
                     gdyn_full[dyn.shape[0] - 1, :, spec.n_par * nmul:].zero_()
             else:
@@ -475,6 +491,7 @@ class _HbvRun(torch.autograd.Function):
             io.gstate_out, io.gstate_series = _ptr(gs), _ptr(gser)
             io.gdyn, io.gsta = _ptr(gdyn_run), _ptr(gsta)
             io.gdyn_zero_fill = zero_fill
+            io.gdyn_rows_before = rows_before
             gstate_in = torch.empty_like(state_in) if state_in.requires_grad else None
             io.gstate_in = _ptr(gstate_in)
             # f3: gradient w.r.t. the forcings (a by-product of the adjoint sweep) and w.r.t. muwts

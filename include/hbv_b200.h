@@ -154,7 +154,11 @@ typedef struct hbv_bwd_io {
     float* gsta;     /* [B, sta_ncol] or NULL                               */
     float* gstate_in;/* [5, B, nmul] or NULL                                */
     int32_t gdyn_zero_fill;
-    int32_t reserved_;
+    int32_t gdyn_rows_before;  /* with gdyn_zero_fill: this many rows in FRONT of gdyn (the no-grad
+                                  warm-up rows of the caller's full [T_total, B, dyn_ncol] plane,
+                                  hbv.py:328) are zeroed by the call as well — inside the
+                                  stage-pipelined adjoint (TMA bulk stores of a zeroed shared-memory
+                                  buffer, paced over its sweep), else by a memset in stream order */
     float* gforcing; /* [T, B, nvar] or NULL: gradient w.r.t. the forcings (P, T, PET columns),
                         summed over the nmul components; ZERO-INITIALISED by the caller.  The
                         rain/snow masks carry no gradient (hbv.py:431-434), T receives it through
