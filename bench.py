@@ -384,6 +384,12 @@ def run_b200(args):
     numa = 'unchanged (HBV_BENCH_NO_NUMA=1)' if os.environ.get('HBV_BENCH_NO_NUMA') == '1' else D.bind_to_gpu_numa_node(local)
     _cabi.load()
     peak, peak_src = measured_peak_gbs()
+    # the shared-gradient all-reduce: the library's one-shot kernel over NVLink peer memory
+    # (csrc/allreduce.cu) when symmetric memory can be set up, else NCCL; HBV_BENCH_ONESHOT=0 keeps NCCL
+    oneshot = False
+    if world > 1 and os.environ.get('HBV_BENCH_ONESHOT', '1') != '0':
+        oneshot = all([D.enable_oneshot_allreduce(w['n_par'] * NMUL + 2, dev)
+                       for w in ({'n_par': 13}, {'n_par': 14})])
 
     def build(wl, B, pin):
         Model = hydrodl2.load_model(wl['model'], ver_name=wl['cls'])
@@ -501,6 +507,12 @@ def run_b200(args):
                 gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
                 step_fn = gstep.replay
                 graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+            elif oneshot and not NO_ALLREDUCE:
+                # the collective is a plain kernel of this library: captured with the step
+                gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=True), warmup=3, device=dev)
+                step_fn = gstep.replay
+                graph_note = ('cuda graph replay of the whole step incl. the one-shot all-reduce of the shared '
+                              'gradient over NVLink peer memory (csrc/allreduce.cu)')
             elif GRAPH_ALLREDUCE and not NO_ALLREDUCE:
                 # the shared-gradient all-reduce is captured with the step (thread-local capture mode:
                 # NCCL's watchdog thread may issue CUDA calls while this thread captures)
@@ -629,6 +641,8 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_of(wl, B, world),
             'run_info': {'ckpt_interval': k_eff(wl, B), 'launch': graph_note, 'eager_ms_per_step': ms_eager,
+                         'shared_grad_allreduce': ('one-shot kernel over NVLink peer memory' if oneshot else
+                                                   ('nccl' if world > 1 else 'none (one GPU)')),
                          'host_affinity': numa},
             'clocks': sampler.summary(), 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_per_step': launches_per_step,
@@ -638,6 +652,9 @@ def run_b200(args):
         emit(line)
     if world > 1:
         import torch.distributed as dist
+        if oneshot and any(o is not None and o.timed_out() for o in D._ONESHOT.values()):
+            print('bench.py: the one-shot all-reduce timed out waiting for a peer — results invalid', file=sys.stderr)
+            return 3
         dist.destroy_process_group()
     return 0
 

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libhbv_b200.so')
 SOURCES = ['hbv_cabi.cu', 'hbv_fwd.cu', 'hbv_bwd.cu', 'uh_route.cu', 'pair_route.cu', 'hbv_adj.cu',
-           'hbv_dense.cu', 'hbv_lean.cu', 'hbv_pipe.cu', 'fill.cu']
+           'hbv_dense.cu', 'hbv_lean.cu', 'hbv_pipe.cu', 'fill.cu', 'allreduce.cu']
 HEADERS = ['hbv_step.cuh', 'hbv_common.cuh', os.path.join('..', '..', 'include', 'hbv_b200.h')]
 
 NVCC_FLAGS = [

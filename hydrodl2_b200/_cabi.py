@@ -95,7 +95,7 @@ EXPORTS = (
     'hbv_b200_launch_count', 'hbv_b200_pair_chunks', 'hbv_b200_pair_route_fwd',
     'hbv_b200_pair_route_bwd', 'hbv_b200_adj_fwd', 'hbv_b200_adj_bwd', 'hbv_b200_auto_ckpt',
     'hbv_b200_dense_launches', 'hbv_b200_lean_launches', 'hbv_b200_pipe_launches', 'hbv_b200_workspace_bytes',
-    'hbv_b200_set_option', 'hbv_b200_get_option', 'hbv_b200_fill_zero', 'hbv_b200_auto_ckpt_desc', 'hbv_b200_copy_cols', 'hbv_b200_memcpy2d',
+    'hbv_b200_set_option', 'hbv_b200_get_option', 'hbv_b200_fill_zero', 'hbv_b200_auto_ckpt_desc', 'hbv_b200_copy_cols', 'hbv_b200_memcpy2d', 'hbv_b200_allreduce_buffer_floats', 'hbv_b200_oneshot_allreduce',
 )
 
 _LIB = None
@@ -139,6 +139,10 @@ def load():
     lib.hbv_b200_fill_zero.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.hbv_b200_copy_cols.restype = C.c_int
     lib.hbv_b200_copy_cols.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.hbv_b200_allreduce_buffer_floats.restype = C.c_int64
+    lib.hbv_b200_allreduce_buffer_floats.argtypes = [C.c_int32, C.c_int32]
+    lib.hbv_b200_oneshot_allreduce.restype = C.c_int
+    lib.hbv_b200_oneshot_allreduce.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.hbv_b200_memcpy2d.restype = C.c_int
     lib.hbv_b200_memcpy2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.hbv_b200_workspace_bytes.argtypes = [C.POINTER(HbvDesc)]

@@ -123,9 +123,72 @@ def bind_to_gpu_numa_node(device_index: int) -> str:
         return f'unchanged ({type(exc).__name__}: {exc})'
 
 
+class OneShotAllReduce:
+    """Sum of a small float32 vector over the ranks of one NVLink / NVSwitch box with the library's
+    own kernel (csrc/allreduce.cu) instead of NCCL: every rank stores its vector into every peer's
+    symmetric buffer and sums what it received — one launch, a few microseconds, capturable in the
+    CUDA graph of a training step.  The symmetric buffer comes from
+    torch.distributed._symmetric_memory (plumbing: allocation + the exchange of peer addresses).
+    `available()` is False where that is not possible; callers then keep NCCL."""
+
+    def __init__(self, n: int, device: torch.device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _cabi as A
+        self.lib, self.C, self.n, self.dev = A.load(), C, int(n), device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        nfl = int(self.lib.hbv_b200_allreduce_buffer_floats(self.world, self.n))
+        self.buf = symm.empty(nfl, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = int(self.hdl.buffer_ptrs_dev)
+        torch.cuda.synchronize(device)
+        dist.barrier()                    # every rank's flags are zero before anyone writes
+
+    def __call__(self, g: torch.Tensor) -> torch.Tensor:
+        """In place, like dist.all_reduce; g: contiguous float32 of `n` elements on the device."""
+        from . import _cabi as A
+        assert g.is_contiguous() and g.dtype == torch.float32 and g.numel() == self.n
+        A.check(self.lib.hbv_b200_oneshot_allreduce(self.ptrs, self.rank, self.world, g.data_ptr(), g.data_ptr(),
+                                                    self.n, torch.cuda.current_stream(self.dev).cuda_stream),
+                'oneshot_allreduce')
+        return g
+
+    def timed_out(self) -> bool:
+        """True if any call gave up waiting for a peer (results are then invalid)."""
+        err = self.buf[-1:].view(torch.int32)
+        return bool(int(err.item()) != 0)
+
+
+_ONESHOT: dict = {}
+
+
+def enable_oneshot_allreduce(n: int, device: torch.device) -> bool:
+    """Route `allreduce_shared_grad` of n-element vectors through OneShotAllReduce (all ranks must
+    call this together).  Returns False — and NCCL stays — if symmetric memory cannot be set up."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    ok = 1
+    try:
+        obj = OneShotAllReduce(n, device)
+    except Exception as exc:     # pragma: no cover - depends on driver / fabric support
+        print(f'hydrodl2_b200.dist: one-shot all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL',
+              flush=True)
+        obj, ok = None, 0
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks or none
+    if int(flag.item()) == 1:
+        _ONESHOT[int(n)] = obj
+        return True
+    return False
+
+
 def allreduce_shared_grad(g: torch.Tensor) -> torch.Tensor:
     """Sum a shared-parameter gradient over ranks (in place); no-op for a single process."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        one = _ONESHOT.get(g.numel()) if g.is_cuda else None
+        if one is not None:
+            return one(g)
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
     return g
 

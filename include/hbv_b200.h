@@ -354,6 +354,15 @@ HBV_API int hbv_b200_copy_cols(float* dst, const float* src, int64_t rows, int64
  * 2 = device -> host.  Measured against copy_cols in scripts/experiments/stage_bw.py. */
 HBV_API int hbv_b200_memcpy2d(float* dst, const float* src, int64_t rows, int64_t row_stride,
                               int32_t col0, int32_t ncols, int32_t kind, void* stream);
+/* One-shot all-reduce (sum) of a small float vector over NVLink peer memory (csrc/allreduce.cu):
+ * `peer_bufs_dev` is a DEVICE array of `world` pointers to the ranks' symmetric comm buffers
+ * (each hbv_b200_allreduce_buffer_floats(world, n) floats, zero-initialised once, peer-mapped —
+ * e.g. torch.distributed._symmetric_memory.rendezvous(...).buffer_ptrs_dev).  Every rank calls it
+ * the same number of times; `out` receives the bit-identical sum on every rank.  A plain kernel
+ * launch: capturable in a CUDA graph (the step counter lives in the buffer). */
+HBV_API int64_t hbv_b200_allreduce_buffer_floats(int32_t world, int32_t n);
+HBV_API int hbv_b200_oneshot_allreduce(float* const* peer_bufs_dev, int32_t rank, int32_t world,
+                                       const float* in, float* out, int32_t n, void* stream);
 /* Experiment / test switches.  Each is read from the environment (HBV_B200_<NAME>) once, when
  * the library is first used, and can be changed at run time here; value -1 = unset (the
  * library's own measured policy decides).  Names (case-insensitive): "lean" (0: never K1s / K2s /
