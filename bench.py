@@ -633,6 +633,16 @@ def run_b200(args):
                        'sample': f"BASELINE configs[0]: hbv forward (no_grad), {wl_c['B']} basins x {wl_c['T']} days, "
                                  f"nmul {NMUL}, best of 2"},
         }
+        if not args.no_cpu_slices:
+            # BASELINE configs 3-5 on bounded slices (reference cost is linear in basins)
+            try:
+                import importlib.util
+                sp = importlib.util.spec_from_file_location('cpu_slices', os.path.join(ROOT, 'scripts', 'cpu_slices.py'))
+                cs = importlib.util.module_from_spec(sp)
+                sp.loader.exec_module(cs)
+                cpu_baseline['slices'] = cs.run(nb=128, nb_hourly=32, nb_adj=16)
+            except Exception as exc:     # pragma: no cover
+                cpu_baseline['slices'] = {'error': f'{type(exc).__name__}: {exc}'}
 
     if rank == 0:
         line = {
@@ -754,6 +764,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-at-scale', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 4 and 5 in at_scale')
+    ap.add_argument('--no-cpu-slices', action='store_true', help='skip the CPU slices of configs 3-5 in cpu_baseline')
     ap.add_argument('--no-graph', dest='graph', action='store_false',
                     help='time the eager step instead of a CUDA-graph replay of it (single GPU: the step '
                          'is ~0.55 ms of kernels, about what one eager Python step costs the host, so the '

@@ -74,8 +74,12 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // WF: write the flux planes (false: the warm-up / `initialize` run — states only, hbv.py:327-346)
 // KS: the state before a step is stored every KS-th step (KS = 1, 2 or 4; LTC % KS == 0, so
 // which steps of an output chunk store is known at compile time)
+// RD = -1: register form with a deeper prefetch (four named buffers of two steps: inputs are
+// requested 4-6 steps before use instead of 2-4) for grids of a few CTAs per SM, where too few warps
+// are resident to hide an HBM round trip (BASELINE config 4's per-GPU share: ncu showed 2.6
+// long_scoreboard stall cycles per issue and 36 % issue-slot utilisation with the 2-buffer form)
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true, int KS = 1>
-__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 6 : 1)
+__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? (RD < 0 ? 3 : 6) : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     static_assert(LTC % KS == 0, "checkpoint interval must divide the output chunk");
     using TR = Traits<VAR>;
@@ -226,44 +230,72 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 
     // registers (RD == 0): two named prefetch buffers of two steps each (see hbv_fwd.cu: loads in
     // flight must not share a scoreboard slot with the values being consumed)
-    In A0, A1, B0, B1;
+    In A0, A1, B0, B1, C0, C1, D0, D1;      // (C*, D*: the deep form only)
     if constexpr (RD > 0) {
 #pragma unroll 1
         for (int q = 0; q < RDS - 1; ++q) issue();
-    } else {
+    } else if constexpr (RD == 0) {
         load(A0); load(A1);
+    } else {
+        load(A0); load(A1); load(B0); load(B1);
     }
-    for (int t0 = 0; t0 < d.T; t0 += LTC) {
-        const int tcn = min(LTC, d.T - t0);
-        if constexpr (RD > 0) {
+    auto reduce_out = [&](int tcn) {          // nmul reduction of the chunk's tile -> [T, B] planes
+        if constexpr (WF) {
+            __syncthreads();
+            if (r_ok && r_tc < tcn) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < LTC; ++u)
-                if (u < tcn) { pop(A0); do_step(A0, u); }
-        } else {
-            load(B0); load(B1);
+                for (int jj = 0; jj < LNM; ++jj) {
+                    const float4 v = *reinterpret_cast<const float4*>(r_src + jj * NFP);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                float* const* pl = io.flux + r_q * 4;
+                pl[0][r_o] = acc.x * inv_nmul;
+                pl[1][r_o] = acc.y * inv_nmul;
+                pl[2][r_o] = acc.z * inv_nmul;
+                if (r_q * 4 + 3 < TR::NFLUX) pl[3][r_o] = acc.w * inv_nmul;
+            }
+            r_o += r_adv;
+            __syncthreads();
+        }
+    };
+    if constexpr (RD < 0) {
+        for (int t0 = 0; t0 < d.T; t0 += 2 * LTC) {
+            int tcn = min(LTC, d.T - t0);
+            load(C0); load(C1);
             do_step(A0, 0);
             if (1 < tcn) do_step(A1, 1);
-            load(A0); load(A1);
+            load(D0); load(D1);
             if (2 < tcn) do_step(B0, 2);
             if (3 < tcn) do_step(B1, 3);
+            reduce_out(tcn);
+            if (t0 + LTC >= d.T) break;
+            tcn = min(LTC, d.T - t0 - LTC);
+            load(A0); load(A1);
+            do_step(C0, 0);
+            if (1 < tcn) do_step(C1, 1);
+            load(B0); load(B1);
+            if (2 < tcn) do_step(D0, 2);
+            if (3 < tcn) do_step(D1, 3);
+            reduce_out(tcn);
         }
-        if constexpr (!WF) continue;
-        __syncthreads();
-        if (r_ok && r_tc < tcn) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int t0 = 0; t0 < d.T; t0 += LTC) {
+            const int tcn = min(LTC, d.T - t0);
+            if constexpr (RD > 0) {
 #pragma unroll
-            for (int jj = 0; jj < LNM; ++jj) {
-                const float4 v = *reinterpret_cast<const float4*>(r_src + jj * NFP);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                for (int u = 0; u < LTC; ++u)
+                    if (u < tcn) { pop(A0); do_step(A0, u); }
+            } else {
+                load(B0); load(B1);
+                do_step(A0, 0);
+                if (1 < tcn) do_step(A1, 1);
+                load(A0); load(A1);
+                if (2 < tcn) do_step(B0, 2);
+                if (3 < tcn) do_step(B1, 3);
             }
-            float* const* pl = io.flux + r_q * 4;
-            pl[0][r_o] = acc.x * inv_nmul;
-            pl[1][r_o] = acc.y * inv_nmul;
-            pl[2][r_o] = acc.z * inv_nmul;
-            if (r_q * 4 + 3 < TR::NFLUX) pl[3][r_o] = acc.w * inv_nmul;
+            reduce_out(tcn);
         }
-        r_o += r_adv;
-        __syncthreads();
     }
     if constexpr (RD > 0) cp_async_wait<0>();
     if (valid && io.state_out != nullptr) {
@@ -618,7 +650,7 @@ template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int RD>
 static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
-    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)RD * (8 + 32 * ND)) * sizeof(float);
+    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)(RD > 0 ? RD : 0) * (8 + 32 * ND)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
     if (io.ckpt == nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
     else if (d.K == 1) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
@@ -657,6 +689,13 @@ int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
     if (lean_small_grid(d, io.ckpt != nullptr)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
+    // up to three 128-thread CTAs per SM (the deep form's residency: one wave): deeper register
+    // prefetch; above, the resident warps hide the latency and the 2-buffer form keeps six CTAs
+    // per SM.  Measured on B200 (fwd with state stores, deep / 2-buffer): `hbv` 2,500 basins 0.307 /
+    // 0.374 ms, hourly 2,500 units x 17,520 h step 23.4 / 25.0 ms; 4,000 basins (a second wave of
+    // the deep form) 0.581 / 0.457 ms.
+    const long long deep_max = opt(OPT_LEAN_DEEP) >= 0 ? opt(OPT_LEAN_DEEP) : 148LL * 3 * 128;
+    if ((long long)d.B * LNM <= deep_max) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, -1>(d, io, st);
     return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 

@@ -9,8 +9,12 @@
  * bind with ctypes from inside `_PBM`.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer owned by the caller (PyTorch);
- *     the library never allocates, never frees and keeps no global state;
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch) unless stated otherwise
+ *     (hbv_b200_copy_cols / memcpy2d also take pinned host pointers); the library never
+ *     allocates and never frees.  Its only process-wide state is bookkeeping that does not
+ *     change results: the launch counters (hbv_b200_*_launches) and the table of experiment
+ *     switches (hbv_b200_set_option; initialised from the environment once) — kernels of
+ *     different families give the same numbers to fp32 round-off;
  *   - all tensors are float32, contiguous in the layouts stated below;
  *   - `stream` is the caller's cudaStream_t (0 = legacy default stream);
  *   - return value: 0 ok, >0 a cudaError_t from launch, <0 argument error

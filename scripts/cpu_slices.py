@@ -21,6 +21,11 @@ import torch  # noqa: E402
 
 def main():
     nb = int(sys.argv[sys.argv.index('--basins') + 1]) if '--basins' in sys.argv else 256
+    print(json.dumps(run(nb), indent=1))
+
+
+def run(nb=256, nb_hourly=64, nb_adj=64):
+    """-> dict of timings; importable (bench.py's cpu_baseline leg runs it on smaller slices)."""
     import bench
     from oracle import hbv_oracle as O
     ref = bench.load_reference()
@@ -54,7 +59,7 @@ def main():
     # ---- config 4: hbv_2_hourly D3; forward on the full 17,520 steps, fwd+bwd on 2,160 steps
     dyn = ['parBETA', 'parK0', 'parBETAET']
     for T, leg in ((17520, 'fwd'), (2160, 'fwd_bwd')):
-        nbh = min(nb, 64)
+        nbh = min(nb, nb_hourly)
         g = torch.Generator().manual_seed(41)
         xh = O.synthetic_forcing(T, nbh, seed=42, hourly=True)
         p0 = torch.rand(T, nbh, 3 * NMUL, generator=g)
@@ -82,7 +87,7 @@ def main():
 
     # ---- config 5: hbv_adj — the reference cannot run; the restatement is timed
     from oracle import hbv_adj_oracle as OA
-    nb5 = min(nb, 64)
+    nb5 = min(nb, nb_adj)
     x5 = O.synthetic_forcing(730, nb5, seed=51)
     p5 = torch.randn(730, nb5, 13 * NMUL + 2, generator=torch.Generator().manual_seed(52)).requires_grad_(True)
     t0 = time.perf_counter()
@@ -95,7 +100,7 @@ def main():
                      'basin_steps_per_s': nb5 * 730 / dt}
     except Exception as exc:
         out['c5'] = {'error': f'{type(exc).__name__}: {exc}'}
-    print(json.dumps(out, indent=1))
+    return out
 
 
 if __name__ == '__main__':

@@ -126,7 +126,7 @@ def _reset_library_options():
     yield
     if torch.cuda.is_available():
         from hydrodl2_b200 import _cabi
-        for name in ('lean', 'pipe', 'pipe_max', 'ring', 'lean_small', 'lean_bwd_ring', 'dense',
+        for name in ('lean', 'pipe', 'pipe_max', 'ring', 'lean_small', 'lean_bwd_ring', 'lean_deep', 'dense',
                      'dense_ns', 'dense_ns_bwd', 'dense_minb', 'ckpt'):
             _cabi.set_option(name, -1)
 
