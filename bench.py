@@ -740,6 +740,9 @@ def _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_ste
             'host_gradient_equals_dense_device_gradient': dense_ok,
             'serial_ms_per_step': ms_serial,
             'pcie_GBps': {'h2d': h2d / (ms_e2e * 1e-3) / 1e9, 'd2h': d2h / (ms_e2e * 1e-3) / 1e9},
+            # how the column blocks crossed PCIe on THIS host (hostio.pick_block_copy times both ways
+            # on the first step: copy engine 2-D copies vs the GPU reading / writing pinned memory)
+            'block_copy': {f'{d}:{n}': m for (d, n), m in pipe.block_copy.items()},
             'what': 'pinned host x_phy + parameters -> device, Model.forward + backward, '
                     'streamflow + loss + parameter gradient -> pinned host; double-buffered on '
                     'upload / compute / download streams (hydrodl2_b200.hostio.PipelinedSteps), '

@@ -333,7 +333,7 @@ enum Opt {
     OPT_RING,             // 0 / 1: force the register / cp.async-ring input path of K1 / K2
     OPT_LEAN_SMALL,       // grid size (lanes) up to which K1s uses its ring form
     OPT_LEAN_BWD_RING,    // 0: K2s register form
-    OPT_LEAN_DEEP,        // grid size (lanes) up to which K1s' register form uses the deeper prefetch
+    OPT_LEAN_DEEP,        // grid size (lanes) up to which K1s' 128-thread form takes its inputs through the chunk ring
     OPT_DENSE,            // 0: never K1d / K2d, 2: wherever the shapes allow (tests), 1 / unset: where they win
     OPT_DENSE_NS, OPT_DENSE_NS_BWD, OPT_DENSE_MINB,
     OPT_CKPT,             // checkpoint interval hbv_b200_auto_ckpt returns (experiments)

@@ -34,6 +34,7 @@ constexpr int LNM = 16;      // components per basin
 // basins per CTA (template LBPB): 8 (128 threads) on large grids; 2 (one warp, so the chunk barrier
 // costs nothing and the CTAs spread over all SMs) on small, latency-bound ones
 constexpr int LTC = 4;       // forward: time steps per output chunk
+constexpr int LNCH = 4;      // forward, chunk-ring form (RD = -1): chunks in the ring
 
 template <int NPAR, int DM, int LAYOUT>
 __host__ __device__ constexpr int lean_col(int i) {
@@ -74,14 +75,19 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // WF: write the flux planes (false: the warm-up / `initialize` run — states only, hbv.py:327-346)
 // KS: the state before a step is stored every KS-th step (KS = 1, 2 or 4; LTC % KS == 0, so
 // which steps of an output chunk store is known at compile time)
-// RD = -1: register form with a deeper prefetch (four named buffers of two steps: inputs are
-// requested 4-6 steps before use instead of 2-4) for grids of a few CTAs per SM, where too few warps
-// are resident to hide an HBM round trip (BASELINE config 4's per-GPU share: ncu showed 2.6
-// long_scoreboard stall cycles per issue and 36 % issue-slot utilisation with the 2-buffer form)
+// RD = -1 (128-thread CTAs): the same cp.async staging at the granularity of an output chunk — a
+// ring of LNCH chunks of LTC steps, one commit group per chunk, filled two to three chunks (8-12
+// steps) ahead; the wait for a chunk rides on the barrier that already closes the previous chunk's
+// nmul reduction.  Why not registers: ptxas puts every LDG of the loop on ONE scoreboard
+// (cuobjdump control codes: write barrier SB5 on all 24 loads of the four-buffer register form), so
+// the first use of the oldest buffer also waits for the loads issued a moment ago — ncu attributed
+// 28 % of the kernel's stall samples to that single wait on BASELINE config 4's per-GPU grid
+// (2.1 warps per scheduler).  cp.async groups complete in FIFO order and are waited for by count.
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true, int KS = 1>
-__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? (RD < 0 ? 3 : 6) : 1)
+__global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? (RD < 0 ? 4 : 6) : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     static_assert(LTC % KS == 0, "checkpoint interval must divide the output chunk");
+    static_assert(RD >= 0 || WF, "the chunk ring rides on the barriers of the flux reduction");
     using TR = Traits<VAR>;
     constexpr int NPAR = TR::NPAR;
     using DS = DynSet<NPAR, DM>;
@@ -167,16 +173,18 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         }
     };
 
-    // ring (RD > 0, one-warp CTA) after the output tile: the warp's inputs of a step are staged by
-    // two cp.async instructions (see the adjoint below for the why):
-    //   A  4 B x 6 lanes   P, T, PET of the two basins               -> slot[4 bl + k]
-    //   B  8 B x 16*ND     the 64 B run of every dynamic parameter   -> slot[8 + 32 k + lane]
-    // read back with one LDS.128 + ND LDS; cp.async.wait_group is followed by __syncwarp() because a
-    // lane reads what other lanes copied.
+    // ring (RD != 0) after the output tile: the CTA's inputs of a step are staged by cp.async
+    // (see the adjoint below for the why):
+    //   A  4 B x 3 LBPB lanes   P, T, PET of the CTA's basins            -> slot[4 bl + k]
+    //   B  8 B x 8 LBPB ND      the 64 B run of every dynamic parameter   -> slot[PARB + NT k + tid]
+    // read back with one LDS.128 + ND LDS; a lane reads what other lanes copied, so the wait for a
+    // group is followed by __syncwarp() (one-warp CTA, RD > 0: one group per step) or rides on the
+    // chunk barrier (RD < 0: one group per output chunk).
+    constexpr int NT = LBPB * LNM;
     constexpr int NDR = DS::NDYN;
-    constexpr int PARB = 8, SLOT = 8 + 32 * NDR;
-    constexpr int NB = (16 * NDR + 31) / 32;
-    constexpr int RDS = RD > 0 ? RD : 2;
+    constexpr int PARB = 4 * LBPB, SLOT = PARB + NT * NDR;
+    constexpr int NB = (8 * LBPB * NDR + NT - 1) / NT;
+    constexpr int RDS = RD > 0 ? RD : (RD < 0 ? LNCH * LTC : 2);
     float* const ring0 = tile + (WF ? LTC * tstride_s : 0);
     float* const ring_end = ring0 + RDS * SLOT;
     float* wp = ring0;
@@ -191,8 +199,8 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     bool actB[NB > 0 ? NB : 1];
 #pragma unroll
     for (int o = 0; o < NB; ++o) {
-        const int gq = o * 32 + tid;
-        actB[o] = gq < 16 * NDR;
+        const int gq = o * NT + tid;
+        actB[o] = gq < 8 * LBPB * NDR;
         const int r = actB[o] ? (gq >> 3) : 0, q = gq & 7;
         const int bb = r / (NDR > 0 ? NDR : 1), k = r - bb * NDR;
         int col = 0;
@@ -200,44 +208,60 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         for (int i = 0; i < NPAR; ++i)
             if (DS::is_dyn(i, 0) && DS::slot(i) == k) col = lean_col<NPAR, DM, LAYOUT>(i);
         srcB[o] = io.dyn + (int64_t)min(b0w + bb, d.B - 1) * d.dyn_ncol + col + 2 * q;
-        dstB[o] = PARB + k * 32 + bb * 16 + 2 * q;
+        dstB[o] = PARB + k * NT + bb * 16 + 2 * q;
     }
-    auto issue = [&]() {             // stage the next time step (the last row again past the end)
-        if (actA) cp_async4(wp + dstA, srcA);
+    auto stage = [&](float* w) {     // copies of the next time step (the last row again past the end)
+        if (actA) cp_async4(w + dstA, srcA);
 #pragma unroll
         for (int o = 0; o < NB; ++o)
-            if (actB[o]) cp_async8(wp + dstB[o], srcB[o]);
-        cp_async_commit();
+            if (actB[o]) cp_async8(w + dstB[o], srcB[o]);
         if (++t_issue < d.T) {
             srcA += sf;
 #pragma unroll
             for (int o = 0; o < NB; ++o) srcB[o] += sd;
         }
+    };
+    auto issue = [&]() {             // one-warp form: one step, one group
+        stage(wp);
+        cp_async_commit();
         wp += SLOT;
         if (wp == ring_end) wp = ring0;
     };
-    auto pop = [&](In& in) {         // oldest staged step
-        cp_async_wait<RDS - 2>();
-        __syncwarp();
-        issue();
-        const float4 f = *reinterpret_cast<const float4*>(rp + 4 * bl);
+    auto issue_chunk = [&]() {       // chunk form: LTC steps, one group
+#pragma unroll
+        for (int u = 0; u < LTC; ++u) stage(wp + u * SLOT);
+        cp_async_commit();
+        wp += LTC * SLOT;
+        if (wp == ring_end) wp = ring0;
+    };
+    auto fetch = [&](In& in, const float* r) {
+        const float4 f = *reinterpret_cast<const float4*>(r + 4 * bl);
         in.P = f.x; in.T = f.y; in.E = f.z;
 #pragma unroll
-        for (int k = 0; k < NDR; ++k) in.raw[k] = rp[PARB + k * 32 + tid];
+        for (int k = 0; k < NDR; ++k) in.raw[k] = r[PARB + k * NT + tid];
+    };
+    auto pop = [&](In& in) {         // oldest staged step
+        cp_async_wait<(RD > 0 ? RD : 2) - 2>();
+        __syncwarp();
+        issue();
+        fetch(in, rp);
         rp += SLOT;
         if (rp == ring_end) rp = ring0;
     };
 
     // registers (RD == 0): two named prefetch buffers of two steps each (see hbv_fwd.cu: loads in
     // flight must not share a scoreboard slot with the values being consumed)
-    In A0, A1, B0, B1, C0, C1, D0, D1;      // (C*, D*: the deep form only)
+    In A0, A1, B0, B1;
     if constexpr (RD > 0) {
 #pragma unroll 1
         for (int q = 0; q < RDS - 1; ++q) issue();
     } else if constexpr (RD == 0) {
         load(A0); load(A1);
     } else {
-        load(A0); load(A1); load(B0); load(B1);
+#pragma unroll 1
+        for (int q = 0; q < LNCH - 1; ++q) issue_chunk();
+        cp_async_wait<LNCH - 2>();
+        __syncthreads();             // chunk 0 has landed for every thread
     }
     auto reduce_out = [&](int tcn) {          // nmul reduction of the chunk's tile -> [T, B] planes
         if constexpr (WF) {
@@ -256,48 +280,36 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
                 if (r_q * 4 + 3 < TR::NFLUX) pl[3][r_o] = acc.w * inv_nmul;
             }
             r_o += r_adv;
+            // chunk form: this thread's copies of the NEXT chunk have landed; the barrier makes
+            // that true for every thread's (groups in flight after it: LNCH - 2)
+            if constexpr (RD < 0) cp_async_wait<LNCH - 2>();
             __syncthreads();
         }
     };
-    if constexpr (RD < 0) {
-        for (int t0 = 0; t0 < d.T; t0 += 2 * LTC) {
-            int tcn = min(LTC, d.T - t0);
-            load(C0); load(C1);
+    for (int t0 = 0; t0 < d.T; t0 += LTC) {
+        const int tcn = min(LTC, d.T - t0);
+        if constexpr (RD > 0) {
+#pragma unroll
+            for (int u = 0; u < LTC; ++u)
+                if (u < tcn) { pop(A0); do_step(A0, u); }
+        } else if constexpr (RD < 0) {
+            issue_chunk();           // into the slot of the chunk every thread finished before the last barrier
+#pragma unroll
+            for (int u = 0; u < LTC; ++u)
+                if (u < tcn) { fetch(A0, rp + u * SLOT); do_step(A0, u); }
+            rp += LTC * SLOT;
+            if (rp == ring_end) rp = ring0;
+        } else {
+            load(B0); load(B1);
             do_step(A0, 0);
             if (1 < tcn) do_step(A1, 1);
-            load(D0); load(D1);
+            load(A0); load(A1);
             if (2 < tcn) do_step(B0, 2);
             if (3 < tcn) do_step(B1, 3);
-            reduce_out(tcn);
-            if (t0 + LTC >= d.T) break;
-            tcn = min(LTC, d.T - t0 - LTC);
-            load(A0); load(A1);
-            do_step(C0, 0);
-            if (1 < tcn) do_step(C1, 1);
-            load(B0); load(B1);
-            if (2 < tcn) do_step(D0, 2);
-            if (3 < tcn) do_step(D1, 3);
-            reduce_out(tcn);
         }
-    } else {
-        for (int t0 = 0; t0 < d.T; t0 += LTC) {
-            const int tcn = min(LTC, d.T - t0);
-            if constexpr (RD > 0) {
-#pragma unroll
-                for (int u = 0; u < LTC; ++u)
-                    if (u < tcn) { pop(A0); do_step(A0, u); }
-            } else {
-                load(B0); load(B1);
-                do_step(A0, 0);
-                if (1 < tcn) do_step(A1, 1);
-                load(A0); load(A1);
-                if (2 < tcn) do_step(B0, 2);
-                if (3 < tcn) do_step(B1, 3);
-            }
-            reduce_out(tcn);
-        }
+        reduce_out(tcn);
     }
-    if constexpr (RD > 0) cp_async_wait<0>();
+    if constexpr (RD != 0) cp_async_wait<0>();
     if (valid && io.state_out != nullptr) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) io.state_out[s * nlane + lane] = S[s];
@@ -646,16 +658,28 @@ static bool lean_bwd_ring(const KDesc& d) {
 constexpr int LRD_F = 12;    // small grids: forward ring depth (steps)
 constexpr int LRD_B = 8;     // small grids: adjoint ring depth
 
+// launch with SMEM bytes of dynamic shared memory; above 48 KB the kernel is opted in once per
+// process (the static is per kernel: the kernel is a template argument, not a function argument)
+template <auto KERN, size_t SMEM, class D, class IO>
+static void lean_go(int grid, int block, cudaStream_t st, const D& d, const IO& io) {
+    if constexpr (SMEM > 48 * 1024) {
+        static const cudaError_t attr = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        (void)attr;
+    }
+    KERN<<<grid, block, SMEM, st>>>(d, io);
+}
+
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int RD>
 static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     constexpr int ND = DynSet<Traits<VAR>::NPAR, DM>::NDYN;
     d.BPB = LBPB;
-    const size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)(RD > 0 ? RD : 0) * (8 + 32 * ND)) * sizeof(float);
+    constexpr int slots = RD > 0 ? RD : (RD < 0 ? LNCH * LTC : 0);
+    constexpr size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)slots * (4 * LBPB + LBPB * LNM * ND)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
-    if (io.ckpt == nullptr) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else if (d.K == 1) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else if (d.K == 2) hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 2><<<grid, LBPB * LNM, smem, st>>>(d, io);
-    else hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 4><<<grid, LBPB * LNM, smem, st>>>(d, io);
+    if (io.ckpt == nullptr) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD>, smem>(grid, LBPB * LNM, st, d, io);
+    else if (d.K == 1) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD>, smem>(grid, LBPB * LNM, st, d, io);
+    else if (d.K == 2) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 2>, smem>(grid, LBPB * LNM, st, d, io);
+    else lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 4>, smem>(grid, LBPB * LNM, st, d, io);
     count_launch();
     count_lean_launch();
     cudaError_t e = cudaGetLastError();
@@ -689,13 +713,15 @@ int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
     if (lean_small_grid(d, io.ckpt != nullptr)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
-    // up to three 128-thread CTAs per SM (the deep form's residency: one wave): deeper register
-    // prefetch; above, the resident warps hide the latency and the 2-buffer form keeps six CTAs
-    // per SM.  Measured on B200 (fwd with state stores, deep / 2-buffer): `hbv` 2,500 basins 0.307 /
-    // 0.374 ms, hourly 2,500 units x 17,520 h step 23.4 / 25.0 ms; 4,000 basins (a second wave of
-    // the deep form) 0.581 / 0.457 ms.
-    const long long deep_max = opt(OPT_LEAN_DEEP) >= 0 ? opt(OPT_LEAN_DEEP) : 148LL * 3 * 128;
-    if ((long long)d.B * LNM <= deep_max) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, -1>(d, io, st);
+    // 128-thread CTAs: inputs through the chunk ring (cp.async, 8 B copies of the parameter runs)
+    // up to `lean_deep` lanes, register prefetch above / when the rows are not 8 B aligned
+    const long long deep_max = opt(OPT_LEAN_DEEP) >= 0 ? opt(OPT_LEAN_DEEP) : (1LL << 62);
+    // (measured on B200, training forward, chunk ring / register form, ms: `hbv` D2 2,500 basins
+    // 0.29 / 0.37, 4,000 0.41 / 0.46, 8,000 0.57 / 0.73, 22,500 (K = 4) 1.54 / 1.74; hourly D3 2,500
+    // units x 17,520 h 8.0 / 9.1.  CTAs of 2 or 4 basins instead of 8 were measured slower on the
+    // hourly grid — step 24.1 / 22.7 / 22.4 ms — and equal within noise on the `hbv` ones.)
+    if ((long long)d.B * LNM <= deep_max && d.dyn_ncol % 2 == 0 && reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0)
+        return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, -1>(d, io, st);
     return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 

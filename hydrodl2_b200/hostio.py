@@ -12,8 +12,9 @@ Column-sparse staging.  The kernels read only part of a packed `parameters` tens
 blocks of the time-varying parameters plus the last row (static values + routing, hbv.py:201-214)
 and the last warm-up row — and most of the dense gradient they return is structural zeros.  Given
 the model's `io_footprint()` the loop uploads exactly those entries (whole rows with a plain async
-copy, column blocks with the library's `hbv_b200_copy_cols`, which lets the GPU read the pinned
-host tensor directly over PCIe) and downloads only the gradient's non-zero entries into a pinned
+copy, column blocks with copy-engine 2-D copies or with the library's `hbv_b200_copy_cols`, which
+lets the GPU read the pinned host tensor directly over PCIe — whichever is faster on this host,
+see BLOCK_COPY) and downloads only the gradient's non-zero entries into a pinned
 host plane that was zeroed once — the host still ends up with the full dense gradient.  BASELINE
 config 2: 985 MB -> ~135 MB over PCIe per step.
 
@@ -43,14 +44,23 @@ def _merge_blocks(blocks):
 # Measured on B200 at BASELINE config 2's shape (two 64-byte blocks per 840-byte row, 49.6 MB;
 # scripts/experiments/stage_bw.py): dma 1.88 ms up / 2.38 ms down, kernel 2.20 / 2.51 ms, the whole
 # tensor 8.8 ms each way — and the copy engine leaves the SMs to the latency-bound kernels.
-BLOCK_COPY = os.environ.get('HBV_B200_BLOCK_COPY', 'dma')
+# The strided copy-engine rate is a property of the HOST, not of the GPU: the same code measured
+# 15.9 / 14.3 GB/s (up / down) on one B200 box and 6.5 / 5.8 GB/s on another whose contiguous copies
+# ran at the same 55 GB/s.  'auto' (default) therefore times both ways once per tensor and
+# direction on the caller's own buffers (`PipelinedSteps`, first step) and keeps the faster one; the
+# SM-driven copy has to win by 15 % to be taken, since it competes with the step's kernels.
+BLOCK_COPY = os.environ.get('HBV_B200_BLOCK_COPY', 'auto')
 
 
-def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cuda.Stream) -> int:
+def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cuda.Stream,
+                mode: Optional[str] = None) -> int:
     """Copy the entries of the [T, B, ncol] float32 tensor `src` named by footprint `fp` into
     `dst` (same shape, both contiguous; either may be pinned host memory) on `stream`.
     fp = {'rows_full': [t, ...], 'col_blocks': [(col0, ncols), ...], 'row_range': (t0, t1)}.
+    mode: 'dma' / 'kernel' for the column blocks (None: BLOCK_COPY, 'auto' counting as 'dma').
     Returns the number of bytes moved."""
+    if mode is None:
+        mode = BLOCK_COPY if BLOCK_COPY in ('dma', 'kernel') else 'dma'
     from . import _cabi as A
     lib = A.load()
     T, B, ncol = src.shape
@@ -70,7 +80,7 @@ def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cu
             off = t0 * B * ncol * 4
             kind = 1 if dst.is_cuda else 2
             for c0, n in _merge_blocks(fp.get('col_blocks', ())):
-                if BLOCK_COPY == 'dma' and dst.is_cuda != src.is_cuda:
+                if mode == 'dma' and dst.is_cuda != src.is_cuda:
                     A.check(lib.hbv_b200_memcpy2d(dst.data_ptr() + off, src.data_ptr() + off, (t1 - t0) * B, ncol,
                                                   c0, n, kind, stream.cuda_stream), 'memcpy2d')
                 else:
@@ -78,6 +88,25 @@ def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cu
                                                    c0, n, stream.cuda_stream), 'copy_cols')
                 moved += (t1 - t0) * B * n * 4
     return moved
+
+
+def pick_block_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cuda.Stream) -> str:
+    """'dma' or 'kernel' for this (tensor, direction, footprint): BLOCK_COPY when it names one,
+    else both timed on `stream` (one warm copy + one timed copy each; the copies are idempotent)."""
+    if BLOCK_COPY in ('dma', 'kernel'):
+        return BLOCK_COPY
+    if not fp.get('col_blocks'):
+        return 'dma'
+    ms = {}
+    for mode in ('dma', 'kernel'):
+        sparse_copy(dst, src, fp, stream, mode)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sparse_copy(dst, src, fp, stream, mode)
+        e1.record(stream)
+        e1.synchronize()
+        ms[mode] = e0.elapsed_time(e1)
+    return 'kernel' if ms['kernel'] < 0.85 * ms['dma'] else 'dma'
 
 
 class PipelinedSteps:
@@ -102,6 +131,7 @@ class PipelinedSteps:
         self.in_fp = dict(in_footprints or {})
         self.out_fp = dict(out_footprints or {})
         self.h2d_bytes = self.d2h_bytes = 0
+        self.block_copy = {}                   # ('in' | 'out', name) -> 'dma' | 'kernel', picked at first use
         self.s_in = torch.cuda.Stream(device)
         self.s_out = torch.cuda.Stream(device)
         self.dev_in = []
@@ -141,7 +171,9 @@ class PipelinedSteps:
             with torch.no_grad():
                 for n, h in host_inputs.items():
                     if n in self.in_fp:
-                        moved += sparse_copy(self.dev_in[k][n], h, self.in_fp[n], self.s_in)
+                        if ('in', n) not in self.block_copy:
+                            self.block_copy['in', n] = pick_block_copy(self.dev_in[k][n], h, self.in_fp[n], self.s_in)
+                        moved += sparse_copy(self.dev_in[k][n], h, self.in_fp[n], self.s_in, self.block_copy['in', n])
                     else:
                         self.dev_in[k][n].copy_(h, non_blocking=True)
                         moved += h.numel() * h.element_size()
@@ -161,7 +193,9 @@ class PipelinedSteps:
             moved = 0
             for n, t in outs.items():
                 if n in self.out_fp:
-                    moved += sparse_copy(hb[n], t.detach(), self.out_fp[n], self.s_out)
+                    if ('out', n) not in self.block_copy:
+                        self.block_copy['out', n] = pick_block_copy(hb[n], t.detach(), self.out_fp[n], self.s_out)
+                    moved += sparse_copy(hb[n], t.detach(), self.out_fp[n], self.s_out, self.block_copy['out', n])
                 else:
                     hb[n].copy_(t.detach(), non_blocking=True)
                     moved += t.numel() * t.element_size()

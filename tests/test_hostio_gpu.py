@@ -56,14 +56,17 @@ def test_pipelined_steps_match_serial():
             assert_close(hbs[i][k], serial[i][k], 1e-7, f'free-running step {i}: {k}')
 
 
-def test_sparse_staging_gives_the_dense_gradient():
+@pytest.mark.parametrize('block_copy', ['auto', 'dma', 'kernel'])
+def test_sparse_staging_gives_the_dense_gradient(block_copy, monkeypatch):
     """Column-sparse staging (hostio.sparse_copy + Model.io_footprint): uploading only the entries
     of `parameters` the kernels read and downloading only the non-zero part of the gradient gives,
     on the host, bit for bit the dense gradient of the whole-tensor loop — with different
     parameters every step and garbage in the entries that are never uploaded."""
     import hydrodl2_b200 as hydrodl2
+    from hydrodl2_b200 import hostio
     from hydrodl2_b200.hostio import PipelinedSteps
     from oracle import hbv_oracle as O
+    monkeypatch.setattr(hostio, 'BLOCK_COPY', block_copy)     # copy engine / SM-driven / timed pick
     dev = torch.device('cuda:0')
     T, B, nmul, warm = 40, 50, 16, 8
     dyn = ['parBETA', 'parBETAET']
@@ -99,6 +102,8 @@ def test_sparse_staging_gives_the_dense_gradient():
         for k in dense[i]:
             assert torch.equal(hb[k], dense[i][k]), f'sparse staging step {i}: {k} differs from the dense loop'
     pipe.drain()
+    assert set(pipe.block_copy) == {('in', 'parameters'), ('out', 'grad')}
+    assert all(m in ('dma', 'kernel') and (block_copy == 'auto' or m == block_copy) for m in pipe.block_copy.values())
     full = 2 * T * B * (13 * nmul + 2) * 4
     assert pipe.h2d_bytes + pipe.d2h_bytes < 0.35 * full
     assert pipe.h2d_bytes == (T * B * 3 + (2 * B * (13 * nmul + 2)) + (T - warm - 1) * B * 2 * nmul) * 4
