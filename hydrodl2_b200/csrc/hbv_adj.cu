@@ -269,6 +269,60 @@ hbv_adj_fwd_kernel(const KDesc d, const AdjFwdPtrs io, const float tol, const in
     }
 }
 
+// One step of the adjoint sweep at the converged end-of-step state y: adds the flux cotangent to
+// gx (= dL/dx_t on entry), solves J^T lambda = gx, returns dL/dp of the step in gp and
+// dL/dx_{t-1} = lambda / dt in gx.
+template <bool BETAET>
+__device__ __forceinline__ void adj_bwd_step(const float (&y)[5], const float (&p)[ADJ_NPAR], float P, float T,
+                                             float PET, float gQ, float inv_dt, float (&gx)[5],
+                                             float (&gp)[ADJ_NPAR]) {
+    AdjEval E;
+    adj_eval<BETAET>(y, p, P, T, PET, E);
+    AdjJac J;
+    adj_jac(E, p, inv_dt, J);
+    // flux Q(x_t, p_t) = q0 + q1 + q2 read at the end-of-step state
+    gx[3] += gQ * E.m3 * (p[HBV_P_K0] * E.u + p[HBV_P_K1]);
+    gx[4] += gQ * E.m4 * p[HBV_P_K2];
+    // J^T lambda = gx (upper block triangular)
+    const float l4 = gx[4] * rcp_nr(J.j44);
+    const float l3 = (gx[3] - J.j43 * l4) * rcp_nr(J.j33);
+    const float l2 = (gx[2] - J.j32 * l3) * rcp_nr(J.j22);
+    const float r0 = gx[0] - J.j20 * l2 - J.j30 * l3;
+    const float r1 = gx[1] - J.j21 * l2 - J.j31 * l3;
+    const float idet = rcp_nr(J.j00 * J.j11 - J.j01 * J.j10);
+    const float l0 = (r0 * J.j11 - J.j10 * r1) * idet;
+    const float l1 = (J.j00 * r1 - J.j01 * r0) * idet;
+    // dL/dp = lambda^T df/dp + gQ dQ/dp, flux by flux
+#pragma unroll
+    for (int i = 0; i < ADJ_NPAR; ++i) gp[i] = 0.f;
+    const float c_melt = (l1 - l0) * E.wm * E.pm;
+    const float c_refr = (l0 - l1) * E.wr * E.pr;
+    gp[HBV_P_CFMAX] = c_melt * E.dT - c_refr * p[HBV_P_CFR] * E.dT;
+    gp[HBV_P_CFR] = -c_refr * p[HBV_P_CFMAX] * E.dT;
+    gp[HBV_P_TT] = -c_melt * p[HBV_P_CFMAX] + c_refr * p[HBV_P_CFR] * p[HBV_P_CFMAX];
+    const float c_pe = l3 - l2;
+    const float c_is = (l2 - l1) + c_pe * E.sw;
+    gp[HBV_P_CWH] = -c_is * E.a * E.SP;
+    const float t_pe = c_pe * E.W * E.bsw * E.sw0;
+    gp[HBV_P_BETA] = t_pe * flog(E.r);
+    float gFC = -fdiv(t_pe * p[HBV_P_BETA], p[HBV_P_FC]) - c_pe * E.e;
+    const float c_et = -l2 * (1.f - E.we) * E.Ep * E.be * E.ef1;
+    const float bexp = BETAET ? p[HBV_P_BETAET] : 1.0f;
+    gp[HBV_P_LP] = -fdiv(c_et * bexp, p[HBV_P_LP]);
+    gFC -= fdiv(c_et * bexp, p[HBV_P_FC]);
+    if constexpr (BETAET) gp[HBV_P_BETAET] = c_et * flog(E.ef0);
+    gp[HBV_P_FC] = gFC;
+    gp[HBV_P_PERC] = (l4 - l3) * (1.f - E.wp);
+    const float c_q01 = gQ - l3;
+    gp[HBV_P_K0] = c_q01 * fmaxf(E.q0a, 0.f);
+    gp[HBV_P_UZL] = -c_q01 * p[HBV_P_K0] * E.u;
+    gp[HBV_P_K1] = c_q01 * E.SUZ;
+    gp[HBV_P_K2] = (gQ - l4) * E.SLZ;
+    // dL/dxt = -lambda^T dG/dxt = lambda / dt
+    gx[0] = l0 * inv_dt; gx[1] = l1 * inv_dt; gx[2] = l2 * inv_dt; gx[3] = l3 * inv_dt; gx[4] = l4 * inv_dt;
+
+}
+
 template <bool BETAET, int DM>
 __global__ void __launch_bounds__(128, HBV_ADJ_BWD_MINB)
 hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
@@ -335,51 +389,8 @@ hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
         const float gQ = gqn * inv_nmul * d.dt;
         load_all(t - 1);
         apply_dyn<NPAR, DM>(d, dynmask, cur, p, dpd);
-        AdjEval E;
-        adj_eval<BETAET>(y, p, cur.P, cur.T, cur.PET, E);
-        AdjJac J;
-        adj_jac(E, p, inv_dt, J);
-        // flux Q(x_t, p_t) = q0 + q1 + q2 read at the end-of-step state
-        gx[3] += gQ * E.m3 * (p[HBV_P_K0] * E.u + p[HBV_P_K1]);
-        gx[4] += gQ * E.m4 * p[HBV_P_K2];
-        // J^T lambda = gx (upper block triangular)
-        const float l4 = gx[4] * rcp_nr(J.j44);
-        const float l3 = (gx[3] - J.j43 * l4) * rcp_nr(J.j33);
-        const float l2 = (gx[2] - J.j32 * l3) * rcp_nr(J.j22);
-        const float r0 = gx[0] - J.j20 * l2 - J.j30 * l3;
-        const float r1 = gx[1] - J.j21 * l2 - J.j31 * l3;
-        const float idet = rcp_nr(J.j00 * J.j11 - J.j01 * J.j10);
-        const float l0 = (r0 * J.j11 - J.j10 * r1) * idet;
-        const float l1 = (J.j00 * r1 - J.j01 * r0) * idet;
-        // dL/dp = lambda^T df/dp + gQ dQ/dp, flux by flux
         float gp[NPAR];
-#pragma unroll
-        for (int i = 0; i < NPAR; ++i) gp[i] = 0.f;
-        const float c_melt = (l1 - l0) * E.wm * E.pm;
-        const float c_refr = (l0 - l1) * E.wr * E.pr;
-        gp[HBV_P_CFMAX] = c_melt * E.dT - c_refr * p[HBV_P_CFR] * E.dT;
-        gp[HBV_P_CFR] = -c_refr * p[HBV_P_CFMAX] * E.dT;
-        gp[HBV_P_TT] = -c_melt * p[HBV_P_CFMAX] + c_refr * p[HBV_P_CFR] * p[HBV_P_CFMAX];
-        const float c_pe = l3 - l2;
-        const float c_is = (l2 - l1) + c_pe * E.sw;
-        gp[HBV_P_CWH] = -c_is * E.a * E.SP;
-        const float t_pe = c_pe * E.W * E.bsw * E.sw0;
-        gp[HBV_P_BETA] = t_pe * flog(E.r);
-        float gFC = -fdiv(t_pe * p[HBV_P_BETA], p[HBV_P_FC]) - c_pe * E.e;
-        const float c_et = -l2 * (1.f - E.we) * E.Ep * E.be * E.ef1;
-        const float bexp = BETAET ? p[HBV_P_BETAET] : 1.0f;
-        gp[HBV_P_LP] = -fdiv(c_et * bexp, p[HBV_P_LP]);
-        gFC -= fdiv(c_et * bexp, p[HBV_P_FC]);
-        if constexpr (BETAET) gp[HBV_P_BETAET] = c_et * flog(E.ef0);
-        gp[HBV_P_FC] = gFC;
-        gp[HBV_P_PERC] = (l4 - l3) * (1.f - E.wp);
-        const float c_q01 = gQ - l3;
-        gp[HBV_P_K0] = c_q01 * fmaxf(E.q0a, 0.f);
-        gp[HBV_P_UZL] = -c_q01 * p[HBV_P_K0] * E.u;
-        gp[HBV_P_K1] = c_q01 * E.SUZ;
-        gp[HBV_P_K2] = (gQ - l4) * E.SLZ;
-        // dL/dxt = -lambda^T dG/dxt = lambda / dt
-        gx[0] = l0 * inv_dt; gx[1] = l1 * inv_dt; gx[2] = l2 * inv_dt; gx[3] = l3 * inv_dt; gx[4] = l4 * inv_dt;
+        adj_bwd_step<BETAET>(y, p, cur.P, cur.T, cur.PET, gQ, inv_dt, gx, gp);
 
         float* gr = gdyn_lane + (int64_t)t * dyn_tstride;
 #pragma unroll
@@ -391,6 +402,140 @@ hbv_adj_bwd_kernel(const KDesc d, const AdjBwdPtrs io) {
         }
     }
     resolve_params<NPAR, DM>(d, io.dyn, nullptr, io.drop, b, j, p, dpd, &lastmask);
+    if (valid) {
+        float* glast = gdyn_lane + (int64_t)(d.T - 1) * dyn_tstride;
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i)
+            if (i < d.n_par && !DS::is_dyn(i, dynmask) && (lastmask & (1u << i))) glast[d.col[i]] = gacc[i] * dpd[i];
+        if (io.gstate_in != nullptr) {
+#pragma unroll
+            for (int s = 0; s < 5; ++s) io.gstate_in[s * nlane + lane] = gx[s];
+        }
+    }
+}
+
+// K3^T, ring form: the same sweep for the standard case (nmul 16, forcing columns prcp / tmean /
+// pet = 0 / 1 / 2 of a 3-wide x_phy, the shipped dynamic set [parBETA, parBETAET], no dropout mask)
+// as one-warp CTAs whose inputs arrive through the cp.async ring of K2s (hbv_lean.cu): a step is
+// staged by FOUR wide copies — 4 B x 8 lanes (P, T, PET, dL/dQ of the warp's two basins), 8 B x 32
+// (the two 64 B parameter runs of each basin), 16 B x 32 + 16 B x 8 (the five 128 B rows of the
+// stored solution) — ARD steps ahead, and read back with one LDS.128 + 7 LDS.  The register form
+// above prefetches ONE step ahead and ncu showed 3.1 long-scoreboard stall cycles per issued
+// instruction at 64 % issue-slot utilisation (profiles/r02_ncu_c5_adj.md).
+constexpr int ARD = 8;
+constexpr int ASLOT = 8 + 32 * (2 + 5);
+
+template <bool BETAET>
+__global__ void __launch_bounds__(32)
+hbv_adj_bwd_ring_kernel(const KDesc d, const AdjBwdPtrs io) {
+    constexpr int NPAR = ADJ_NPAR;
+    constexpr int DM = DM_D2;
+    using DS = DynSet<NPAR, DM>;
+    extern __shared__ __align__(16) float ringmem[];
+    const int tid = threadIdx.x;
+    const int bl = tid >> 4, j = tid & 15;
+    const int b0w = blockIdx.x * 2;
+    const int b_raw = b0w + bl;
+    const bool valid = b_raw < d.B;
+    const int b = valid ? b_raw : d.B - 1;
+    const int64_t lane = (int64_t)b * 16 + j;
+    const int64_t nlane = (int64_t)d.B * 16;
+
+    float p[NPAR], dpd[NPAR], gacc[NPAR];
+    uint32_t lastmask = 0;
+    const uint32_t dynmask = resolve_params<NPAR, DM>(d, io.dyn, nullptr, nullptr, b, j, p, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) { dpd[i] = 0.f; gacc[i] = 0.f; }
+    const int64_t dyn_tstride = (int64_t)d.B * d.dyn_ncol;
+    float* gdyn_lane = io.gdyn + (int64_t)b * d.dyn_ncol + j;
+    constexpr float inv_nmul = 1.0f / 16.0f;
+    const float inv_dt = d.inv_dt;
+
+    float gx[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) gx[s] = io.gstate_out ? __ldg(io.gstate_out + s * nlane + lane) : 0.f;
+
+    // ---- ring staging (sources positioned on step T-1, walked backwards)
+    constexpr int PARB = 8, STB = 8 + 32 * 2;
+    float* const ring_end = ringmem + ARD * ASLOT;
+    float* wp = ringmem;
+    const float* rp = ringmem;
+    const int nbw = min(2, d.B - b0w);
+    const int kA = tid & 15, bbA = tid >> 4;
+    const bool actA = kA < 3 || (kA == 3 && io.gqsim != nullptr);
+    const int64_t rowA = (int64_t)(d.T - 1) * d.B + min(b0w + bbA, d.B - 1);
+    const float* srcA = (kA < 3) ? io.forcing + rowA * 3 + kA : (io.gqsim ? io.gqsim + rowA : io.forcing);
+    const int64_t strA = (kA < 3) ? (int64_t)d.B * 3 : (int64_t)d.B;
+    const int dstA = 4 * bbA + kA;
+    // B: run r = tid >> 3 of the warp's four (basin, parameter) runs, 8 B piece q = tid & 7
+    const int rB = tid >> 3, qB = tid & 7;
+    const int bbB = rB >> 1, kB = rB & 1;
+    const int colB = kB == 0 ? d.col[HBV_P_BETA] : d.col[HBV_P_BETAET];
+    const float* srcB = io.dyn + ((int64_t)(d.T - 1) * d.B + min(b0w + bbB, d.B - 1)) * d.dyn_ncol + colB + 2 * qB;
+    const int dstB = PARB + kB * 32 + bbB * 16 + 2 * qB;
+    const int sC = tid >> 3, qC = tid & 7;
+    const bool actC = 4 * qC < 16 * nbw;
+    const float* srcC = io.ysol + ((int64_t)(d.T - 1) * 5 + sC) * nlane + (int64_t)b0w * 16 + 4 * qC;
+    const float* srcD = io.ysol + ((int64_t)(d.T - 1) * 5 + 4) * nlane + (int64_t)b0w * 16 + 4 * qC;
+    const bool actD = actC && tid < 8;
+    const int dstC = STB + sC * 32 + 4 * qC, dstD = STB + 4 * 32 + 4 * qC;
+    const int64_t strC = 5 * nlane;
+    int t_stage = d.T - 1;
+    auto issue = [&]() {             // stage the inputs of the next step of the sweep (if any)
+        if (t_stage >= 0) {
+            if (actA) cp_async4(wp + dstA, srcA);
+            cp_async8(wp + dstB, srcB);
+            if (actC) cp_async16(wp + dstC, srcC);
+            if (actD) cp_async16(wp + dstD, srcD);
+            srcA -= strA; srcB -= dyn_tstride; srcC -= strC; srcD -= strC;
+        }
+        --t_stage;
+        cp_async_commit();
+        wp += ASLOT;
+        if (wp == ring_end) wp = ringmem;
+    };
+#pragma unroll 1
+    for (int q = 0; q < ARD - 1; ++q) issue();
+
+    const bool has_gq = io.gqsim != nullptr;
+#pragma unroll 1
+    for (int t = d.T - 1; t >= 0; --t) {
+        cp_async_wait<ARD - 2>();
+        __syncwarp();                // the oldest step has landed for every lane; the slot refilled
+        issue();                     // now was read by every lane one iteration ago
+        const float4 f = *reinterpret_cast<const float4*>(rp + 4 * bl);
+        StepIn<DS::NS> cur;
+        cur.P = f.x; cur.T = f.y; cur.PET = f.z;
+        cur.raw[0] = rp[PARB + tid];
+        cur.raw[1] = rp[PARB + 32 + tid];
+        float y[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) y[s] = rp[STB + s * 32 + tid];
+        rp += ASLOT;
+        if (rp == ring_end) rp = ringmem;
+        if (io.zero_fill) {          // (see the register form)
+            if (t < d.T - 1 && nbw > 0) {
+                float2* z = reinterpret_cast<float2*>(io.gdyn + ((int64_t)t * d.B + b0w) * d.dyn_ncol);
+                const int n2 = (nbw * d.dyn_ncol) >> 1;
+                for (int e = tid; e < n2; e += 32) z[e] = make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+        }
+        const float gQ = has_gq ? f.w * inv_nmul * d.dt : 0.f;
+        apply_dyn<NPAR, DM>(d, dynmask, cur, p, dpd);
+        float gp[NPAR];
+        adj_bwd_step<BETAET>(y, p, cur.P, cur.T, cur.PET, gQ, inv_dt, gx, gp);
+        float* gr = gdyn_lane + (int64_t)t * dyn_tstride;
+#pragma unroll
+        for (int i = 0; i < NPAR; ++i) {
+            if (i < d.n_par) {
+                if (DS::is_dyn(i, dynmask)) { if (valid) gr[d.col[i]] = gp[i] * dpd[i]; }
+                else gacc[i] += gp[i];
+            }
+        }
+    }
+    cp_async_wait<0>();
+    resolve_params<NPAR, DM>(d, io.dyn, nullptr, nullptr, b, j, p, dpd, &lastmask);
     if (valid) {
         float* glast = gdyn_lane + (int64_t)(d.T - 1) * dyn_tstride;
 #pragma unroll
@@ -442,6 +587,11 @@ int adj_fwd_dispatch(const hbv_desc_t* desc, const hbv_adj_fwd_io_t* io, cudaStr
     KDesc d;
     int rc = adj_prepare(desc, d);
     if (rc) return rc;
+    // one-warp CTAs at nmul 16: the chunk barrier of the flow staging then couples no warps whose
+    // Newton counts differ (10,000 basins x 730 days, forward alone: 2.79 / 2.82 / 2.84 ms with 2 / 4 / 8
+    // basins per CTA)
+    if (opt(OPT_ADJ_BPB) > 0 && opt(OPT_ADJ_BPB) * d.nmul <= 128) d.BPB = (int)opt(OPT_ADJ_BPB);
+    else if (d.nmul == 16) d.BPB = 2;
     AdjFwdPtrs p{io->forcing, io->dyn, io->drop, io->state_in, io->state_out, io->qsim, io->ysol, io->stats};
     const float tol = desc->adj_tol > 0.f ? desc->adj_tol : 1e-3f;
     const int maxu = desc->adj_max_updates > 0 ? desc->adj_max_updates : 8;
@@ -468,6 +618,20 @@ int adj_bwd_dispatch(const hbv_desc_t* desc, const hbv_adj_bwd_io_t* io, cudaStr
         p.zero_fill = 1;
     }
     const int dm = static_dynmask(d, io->drop != nullptr);
+    // standard case: the ring form (wide cp.async copies: even rows, 8 / 16 B-aligned bases)
+    if (dm == DM_D2 && d.nmul == 16 && d.nvar == 3 && d.i_prcp == 0 && d.i_tmean == 1 && d.i_pet == 2 &&
+        d.dyn_ncol % 2 == 0 && d.col[HBV_P_BETA] % 2 == 0 && d.col[HBV_P_BETAET] % 2 == 0 &&
+        reinterpret_cast<uintptr_t>(io->dyn) % 8 == 0 && reinterpret_cast<uintptr_t>(io->ysol) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(io->gdyn) % 8 == 0 && opt(OPT_RING) != 0) {
+        const int grid = (d.B + 1) / 2;
+        const size_t smem = (size_t)ARD * ASLOT * sizeof(float);
+        if (desc->betaet) hbv_adj_bwd_ring_kernel<true><<<grid, 32, smem, st>>>(d, p);
+        else hbv_adj_bwd_ring_kernel<false><<<grid, 32, smem, st>>>(d, p);
+        count_launch();
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) set_error(cudaGetErrorString(e));
+        return (int)e;
+    }
     if (desc->betaet) {
         if (dm == 0) return launch_adj_bwd<true, 0>(d, p, st);
         if (dm == DM_D2) return launch_adj_bwd<true, DM_D2>(d, p, st);

@@ -337,6 +337,7 @@ enum Opt {
     OPT_DENSE,            // 0: never K1d / K2d, 2: wherever the shapes allow (tests), 1 / unset: where they win
     OPT_DENSE_NS, OPT_DENSE_NS_BWD, OPT_DENSE_MINB,
     OPT_CKPT,             // checkpoint interval hbv_b200_auto_ckpt returns (experiments)
+    OPT_ADJ_BPB,          // basins per CTA of K3's forward (experiments; unset: by measurement)
     OPT_COUNT
 };
 long long opt(Opt o);

@@ -122,7 +122,11 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     const float* pf = io.forcing + (int64_t)b * 3;
     const float* pd = io.dyn + (int64_t)b * d.dyn_ncol + j;
     const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
-    float* pk = CK ? io.ckpt + lane : nullptr;       // (t, state) planes are nlane apart
+    // (t, state) planes are nlane apart.  A warp-major store [warp][t][state][32] — 640 contiguous
+    // bytes per warp and step instead of five 128 B rows 4 nlane bytes apart — was measured at
+    // BASELINE config 4's per-GPU grid: K1s 8.02 -> 7.82 ms, K2s 12.29 -> 12.14 ms (with the stores
+    // kept in L2 altogether K1s takes 7.27 ms); not worth a second layout in every kernel family.
+    float* pk = CK ? io.ckpt + lane : nullptr;
 
     struct In { float P, T, E; float raw[ND]; };
     int t_issue = 0;

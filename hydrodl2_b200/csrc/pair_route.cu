@@ -108,8 +108,11 @@ pair_conv_kernel(const PDesc d, const float* __restrict__ uh, const float* __res
                  const int* __restrict__ col, const float* __restrict__ scale, float* __restrict__ y) {
     extern __shared__ float sm[];
     const int Mp = round_up(d.M, PR);
+    const int nrow = PTT + Mp - 1;
     float* us = sm;                       // [Mp][PPB]
-    float* xs = sm + Mp * PPB;            // [PTT + Mp - 1][PPB]
+    // [nrow + 1][PPB]: the window rows plus one pad row (in front for the forward, behind for the
+    // adjoint) that the last, unused window refill reads — no index clamp in the tap loop
+    float* xs = sm + Mp * PPB + (REV ? 0 : PPB);
     const int px = threadIdx.x % PPB;
     const int ty = threadIdx.x / PPB;
     const int p = blockIdx.x * PPB + px;
@@ -119,44 +122,49 @@ pair_conv_kernel(const PDesc d, const float* __restrict__ uh, const float* __res
     float sc = 0.f;
     if (pv) { c = col ? col[p] : p; sc = scale ? scale[c] : 1.f; }
     for (int k = ty; k < Mp; k += PTY) us[k * PPB + px] = (pv && k < d.M) ? uh[(int64_t)k * d.P + p] : 0.f;
-    const int nrow = PTT + Mp - 1;
     // window rows r = 0..nrow-1 map to time  t0 - (Mp-1) + r  (forward)  /  t0 + r  (reverse)
     for (int r = ty; r < nrow; r += PTY) {
         const int t = REV ? (t0 + r) : (t0 - (Mp - 1) + r);
         xs[r * PPB + px] = (pv && t >= 0 && t < d.T) ? src[(int64_t)t * src_stride + c] * sc : 0.f;
     }
+    if (ty == 0) xs[(REV ? nrow : -1) * PPB + px] = 0.f;
     __syncthreads();
     const int i0 = ty * PR;
     float acc[PR], w[PR];
 #pragma unroll
     for (int r = 0; r < PR; ++r) acc[r] = 0.f;
+    const float* up = us + px;
     if constexpr (!REV) {
         // logical window W_k[r] = xs[i0 + r + Mp-1-k], kept in register w[(r - k) mod PR]
 #pragma unroll
         for (int r = 0; r < PR; ++r) w[r] = xs[(i0 + r + Mp - 1) * PPB + px];
+        const float* xp = xs + (i0 + Mp - 2) * PPB + px;              // W_1[0]
         for (int kb = 0; kb < Mp; kb += PR) {
 #pragma unroll
             for (int kk = 0; kk < PR; ++kk) {
-                const float u = us[(kb + kk) * PPB + px];
+                const float u = up[kk * PPB];
 #pragma unroll
                 for (int r = 0; r < PR; ++r) acc[r] = fmaf(u, w[(r - kk + PR) % PR], acc[r]);
-                const int nx = max(i0 + Mp - 2 - (kb + kk), 0);      // W_{k+1}[0] (unused after the last tap)
-                w[PR - 1 - kk] = xs[nx * PPB + px];
+                w[PR - 1 - kk] = xp[-kk * PPB];                       // W_{k+1}[0] (row -1 after the last tap)
             }
+            up += PR * PPB;
+            xp -= PR * PPB;
         }
     } else {
         // W_k[r] = xs[i0 + r + k], kept in register w[(r + k) mod PR]
 #pragma unroll
         for (int r = 0; r < PR; ++r) w[r] = xs[(i0 + r) * PPB + px];
+        const float* xp = xs + (i0 + PR) * PPB + px;                  // W_1[PR-1]
         for (int kb = 0; kb < Mp; kb += PR) {
 #pragma unroll
             for (int kk = 0; kk < PR; ++kk) {
-                const float u = us[(kb + kk) * PPB + px];
+                const float u = up[kk * PPB];
 #pragma unroll
                 for (int r = 0; r < PR; ++r) acc[r] = fmaf(u, w[(r + kk) % PR], acc[r]);
-                const int nx = min(i0 + PR + kb + kk, nrow - 1);      // W_{k+1}[PR-1]
-                w[kk] = xs[nx * PPB + px];
+                w[kk] = xp[kk * PPB];                                  // W_{k+1}[PR-1] (row nrow after the last tap)
             }
+            up += PR * PPB;
+            xp += PR * PPB;
         }
     }
     if (pv) {
@@ -251,8 +259,8 @@ pair_duh_kernel(const PDesc d, const float* __restrict__ gsrc, int g_stride, con
     const int Mp = round_up(d.M, DK);
     const int nrow = PTT + Mp - 1;
     float* gs = sm;                        // [PTT][PPB]
-    float* xs = gs + PTT * PPB;            // [PTT + Mp - 1][PPB]
-    float* du = xs + nrow * PPB;           // [DNS][Mp][PPB]
+    float* xs = gs + PTT * PPB;            // [nrow + 1][PPB] (one zero pad row behind: the last window refill)
+    float* du = xs + (nrow + 1) * PPB;     // [DNS][Mp][PPB]
     const int px = threadIdx.x % PPB;
     const int ty = threadIdx.x / PPB;
     const int p = blockIdx.x * PPB + px;
@@ -265,6 +273,7 @@ pair_duh_kernel(const PDesc d, const float* __restrict__ gsrc, int g_stride, con
         gc = gcol ? gcol[p] : p; gsc = gscale ? gscale[gc] : 1.f;
     }
     for (int e = ty; e < DNS * Mp; e += PTY) du[e * PPB + px] = 0.f;
+    if (ty == 0) xs[nrow * PPB + px] = 0.f;
     const int ngrp = Mp / DK, nitem = ngrp * DNS;
     const int tbeg = ch * d.tchunk;
     const int tend = min(d.T, tbeg + d.tchunk);
@@ -287,16 +296,18 @@ pair_duh_kernel(const PDesc d, const float* __restrict__ gsrc, int g_stride, con
             float acc[DK], v[DK];
 #pragma unroll
             for (int q = 0; q < DK; ++q) { acc[q] = 0.f; v[q] = xs[(ib + Mp - 1 - k0 - q) * PPB + px]; }
+            const float* gp = gs + ib * PPB + px;
+            const float* xp = xs + (ib + Mp - k0) * PPB + px;          // V_{ib+1}[0]
             for (int i8 = 0; i8 < DTS; i8 += DK) {
 #pragma unroll
                 for (int ii = 0; ii < DK; ++ii) {
-                    const int i = ib + i8 + ii;
-                    const float g = gs[i * PPB + px];
+                    const float g = gp[ii * PPB];
 #pragma unroll
                     for (int q = 0; q < DK; ++q) acc[q] = fmaf(g, v[(q - ii + DK) % DK], acc[q]);
-                    const int nx = min(i + Mp - k0, nrow - 1);        // V_{i+1}[0]
-                    v[DK - 1 - ii] = xs[nx * PPB + px];
+                    v[DK - 1 - ii] = xp[ii * PPB];                     // V_{i+1}[0] (the pad row at the very end)
                 }
+                gp += DK * PPB;
+                xp += DK * PPB;
             }
             float* dst = du + ((size_t)sl * Mp + k0) * PPB + px;
 #pragma unroll
@@ -388,11 +399,11 @@ pair_uh_bwd_kernel(const PDesc d, const float* __restrict__ par, const float* __
 
 static size_t conv_smem(const PDesc& d) {
     const int Mp = round_up(d.M, PR);
-    return (size_t)(Mp + PTT + Mp - 1) * PPB * sizeof(float);
+    return (size_t)(Mp + PTT + Mp) * PPB * sizeof(float);
 }
 static size_t duh_smem(const PDesc& d) {
     const int Mp = round_up(d.M, DK);
-    return (size_t)(PTT + PTT + Mp - 1 + DNS * Mp) * PPB * sizeof(float);
+    return (size_t)(PTT + PTT + Mp + DNS * Mp) * PPB * sizeof(float);
 }
 // the largest tap count needs more than the 48 KB a kernel gets without asking (once per process)
 static void pair_smem_opt_in() {

@@ -371,10 +371,12 @@ HBV_API int hbv_b200_oneshot_allreduce(float* const* peer_bufs_dev, int32_t rank
  * the library is first used, and can be changed at run time here; value -1 = unset (the
  * library's own measured policy decides).  Names (case-insensitive): "lean" (0: never K1s / K2s /
  * K1p / K2p), "pipe" (0: never K1p / K2p), "pipe_max" (largest grid in lanes for K1p / K2p),
- * "ring" (0 / 1: force register / cp.async-ring inputs in K1 / K2), "lean_small",
- * "lean_bwd_ring", "dense" (0: never K1d / K2d, 2: wherever the shapes allow), "dense_ns",
- * "dense_ns_bwd", "dense_minb", "ckpt" (the interval hbv_b200_auto_ckpt returns).  Returns 0, or HBV_E_SHAPE for an unknown name
- * (get: INT64_MIN). */
+ * "ring" (0 / 1: force register / cp.async-ring inputs in K1 / K2; 0 also keeps K3's adjoint on
+ * its register form), "lean_small", "lean_bwd_ring", "lean_deep" (largest grid in lanes whose
+ * 128-thread K1s takes its inputs through the chunk ring; 0: register prefetch), "dense" (0: never
+ * K1d / K2d, 2: wherever the shapes allow), "dense_ns", "dense_ns_bwd", "dense_minb", "ckpt" (the
+ * interval hbv_b200_auto_ckpt returns), "adj_bpb" (basins per CTA of K3's forward).  Returns 0, or
+ * HBV_E_SHAPE for an unknown name (get: INT64_MIN). */
 HBV_API int hbv_b200_set_option(const char* name, int64_t value);
 HBV_API int64_t hbv_b200_get_option(const char* name);
 /* launches of the stage-pipelined kernels K1p / K2p (csrc/hbv_pipe.cu; a subset of lean_launches) */

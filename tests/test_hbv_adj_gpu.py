@@ -51,6 +51,36 @@ def test_adj_flow_and_gradient(case):
     assert 1 <= stats[0] <= m.newton_max_updates and stats[1] == 0, stats
 
 
+@pytest.mark.parametrize('B', [7, 64])
+def test_adj_ring_adjoint_matches_register_form(B):
+    """The standard case (nmul 16, [parBETA, parBETAET]) takes the cp.async-ring adjoint
+    (hbv_adj_bwd_ring_kernel); option ring = 0 keeps the register-prefetch kernel.  Same step
+    arithmetic (one device function), so the gradients agree to fp32 contraction noise; the oracle
+    leg of the ring form is `test_adj_flow_and_gradient[d2_warm]`."""
+    from hydrodl2_b200 import _cabi
+    from oracle import hbv_oracle as O
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    T, nmul, warm = 61, 16, 11
+    x = O.synthetic_forcing(T, B, seed=31).to(dev)
+    gen = torch.Generator().manual_seed(32)
+    p = torch.randn(T, B, 13 * nmul + 2, generator=gen).to(dev)
+    cot = torch.randn(T - warm, B, 1, generator=gen).to(dev)
+    grads = {}
+    for ring in (-1, 0):
+        _cabi.set_option('ring', ring)
+        M = hydrodl2.load_model('hbv_adj', ver_name='HbvAdj')
+        m = M({'warm_up': warm, 'dynamic_params': {'HbvAdj': ['parBETA', 'parBETAET']}, 'nmul': nmul}, device=dev)
+        pg = p.clone().requires_grad_(True)
+        out = m({'x_phy': x}, pg)
+        (out['flow_sim'] * cot).sum().backward()
+        grads[ring] = pg.grad
+    assert torch.isfinite(grads[-1]).all()
+    assert_close(grads[-1], grads[0], 5e-6, f'K3 adjoint ring vs register form, B={B}')
+    # structural zeros of the dense plane are exact zeros in both (fused zero fill)
+    assert torch.equal(grads[-1] == 0, grads[0] == 0)
+
+
 def test_adj_no_routing():
     case = CASES[1]
     m, out, pg, ref, p64 = _run(case, routing=False)
