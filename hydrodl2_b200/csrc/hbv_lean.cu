@@ -528,16 +528,18 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
 #pragma unroll
         for (int f = 0; f < HBV_MAX_FLUX; ++f) gF[f] = 0.f;
         gF[HBV_F_QSIM] = cur.q * inv_nmul;
+        // the adjoint stages only ever add to gp[]: a time-invariant parameter's terms go straight
+        // into its running sum (one FFMA per term instead of a per-step sum plus an FADD)
         float gp[NPAR];
 #pragma unroll
-        for (int i = 0; i < NPAR; ++i) gp[i] = 0.f;
+        for (int i = 0; i < NPAR; ++i) gp[i] = DS::is_dyn(i, 0) ? -0.f : gacc[i];     // (-0 + x folds to x, +0 + x does not)
         float gX[3];
-        step_bwd<VAR, BETAET>(gS, gF, p, PET, lc, tp, gp, gX);
+        step_bwd<VAR, BETAET, true>(gS, gF, p, PET, lc, tp, gp, gX);      // (cotangent on the streamflow series only)
 
 #pragma unroll
         for (int i = 0; i < NPAR; ++i) {
             if (DS::is_dyn(i, 0)) { if (valid) pg[lean_col<NPAR, DM, LAYOUT>(i)] = gp[i] * dpd[DS::slot(i)]; }
-            else gacc[i] += gp[i];
+            else gacc[i] = gp[i];
         }
         pg -= sd;
     };

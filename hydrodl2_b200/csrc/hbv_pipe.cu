@@ -599,20 +599,20 @@ hbv_bwd_pipe_kernel(const KDesc d, const BwdPtrs io) {
 #pragma unroll
             for (int f = 0; f < HBV_MAX_FLUX; ++f) gF[f] = 0.f;
             gF[HBV_F_QSIM] = r_rs[4 * bl + 3] * inv_nmul;
-            float gp[NPAR];
+            float gp[NPAR];      // (time-invariant parameters: terms go straight into the running sum)
 #pragma unroll
-            for (int k = 0; k < NPAR; ++k) gp[k] = 0.f;
+            for (int k = 0; k < NPAR; ++k) gp[k] = DS::is_dyn(k, 0) ? -0.f : gacc[k];    // (-0 + x folds to x, +0 + x does not)
             float gRE, gW, gPET, gP, gT;
-            resp_bwd<VAR>(gS[3], gS[4], gF, pa, lc, t0, gp, gRE);
-            soil_bwd<VAR, BETAET>(gS[2], gS[4], gRE, gF, pa, pet1, lc, t0, gp, gW, gPET);
-            snow_bwd<VAR>(gS[0], gS[1], gW, gF, pa, lc, t0, gp, gP, gT);
+            resp_bwd<VAR, true>(gS[3], gS[4], gF, pa, lc, t0, gp, gRE);       // (cotangent on the streamflow series only)
+            soil_bwd<VAR, BETAET, true>(gS[2], gS[4], gRE, gF, pa, pet1, lc, t0, gp, gW, gPET);
+            snow_bwd<VAR, true>(gS[0], gS[1], gW, gF, pa, lc, t0, gp, gP, gT);
 #pragma unroll
             for (int k = 0; k < NPAR; ++k) {
                 if (DS::is_dyn(k, 0)) {
                     const float dd = par_stage(k) == 2 ? ddc[DS::slot(k)] : (par_stage(k) == 1 ? hd1[DS::slot(k)] : hd2[DS::slot(k)]);
                     if (valid) pg[pipe_col<NPAR, DM, LAYOUT>(k)] = gp[k] * dd;
                 } else {
-                    gacc[k] += gp[k];
+                    gacc[k] = gp[k];
                 }
             }
             pg -= sd;

@@ -311,11 +311,17 @@ __device__ __forceinline__ float min_w(float a, float b) {
     return (a < b) ? 1.f : ((a > b) ? 0.f : 0.5f);
 }
 
+// QO (template flag of the adjoint stages): the caller's only cotangent is on the streamflow
+// series (gF[HBV_F_QSIM]); every other gF entry is a literal zero there, but `0.f + x` is not `x`
+// under IEEE rules (-0), so the compiler keeps the additions — 11 instructions per step in K2s.
+template <bool QO>
+__device__ __forceinline__ float cot_add(float g, float x) { return QO ? x : g + x; }
+
 // ---- adjoint stages (reverse order: resp -> soil -> snow) -------------------------------------
 // resp_bwd: in  gSUZ (= dL/dSUZ after the step), gSLZ (= dL/dSLZ after the step), gF;
 //           out gSUZ (before the step), gSLZ = dL/dSLZa (the soil stage's output), and
 //           gRE = d(SUZ1)-path gradient shared by recharge and excess (already "* dt").
-template <int VAR>
+template <int VAR, bool QO = false>
 __device__ __forceinline__ void resp_bwd(float& gSUZ, float& gSLZ, const float (&gF)[HBV_MAX_FLUX],
                                          const float (&p)[Traits<VAR>::NPAR], const LaneConst& c,
                                          const Tape& tp, float (&gp)[Traits<VAR>::NPAR], float& gRE) {
@@ -323,9 +329,9 @@ __device__ __forceinline__ void resp_bwd(float& gSUZ, float& gSLZ, const float (
     const float dt = c.dt, inv_dt = c.inv_dt, nz = c.nearzero;
     auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };       // "* dt"
     auto ID = [&](float x) { return TR::HOURLY ? x * inv_dt : x; };  // "/ dt"
-    const float gQ0 = gF[HBV_F_Q0] + gF[HBV_F_QSIM];
-    const float gQ1 = gF[HBV_F_Q1] + gF[HBV_F_QSIM];
-    const float gQ2 = gF[HBV_F_Q2] + gF[HBV_F_QSIM];
+    const float gQ0 = cot_add<QO>(gF[HBV_F_Q0], gF[HBV_F_QSIM]);
+    const float gQ1 = cot_add<QO>(gF[HBV_F_Q1], gF[HBV_F_QSIM]);
+    const float gQ2 = cot_add<QO>(gF[HBV_F_Q2], gF[HBV_F_QSIM]);
     const float gSUZ4 = gSUZ;
     const float gSLZ3 = gSLZ;
     // SLZ3 = SLZ2 - Q2*dt ; Q2 = K2*SLZ2
@@ -345,7 +351,7 @@ __device__ __forceinline__ void resp_bwd(float& gSUZ, float& gSLZ, const float (
         }
     }
     // SLZ1 = SLZa + PERC*dt
-    float gPERC = gF[HBV_F_PERC] + D(gSLZ1);
+    float gPERC = cot_add<QO>(gF[HBV_F_PERC], D(gSLZ1));
     // SUZ4 = SUZ3 - Q1*dt ; Q1 = K1*SUZ3
     const float gQ1t = gQ1 - D(gSUZ4);
     gp[HBV_P_K1] += gQ1t * tp.SUZ3;
@@ -372,7 +378,7 @@ __device__ __forceinline__ void resp_bwd(float& gSUZ, float& gSLZ, const float (
 // soil_bwd: in  gSM (= dL/dSM after the step), gSLZa (from resp_bwd), gRE, gF;
 //           out gSM (before the step), gSLZ (= dL/dSLZ at the start of the step: variants without
 //           capillary rise pass gSLZa through), gW = dL/d(RAIN + tosoil), gPET.
-template <int VAR, bool BETAET>
+template <int VAR, bool BETAET, bool QO = false>
 __device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, const float (&gF)[HBV_MAX_FLUX],
                                          const float (&p)[Traits<VAR>::NPAR], float PET, const LaneConst& c,
                                          const Tape& tp, float (&gp)[Traits<VAR>::NPAR],
@@ -384,8 +390,8 @@ __device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, con
     const float gIE = gF[HBV_F_QSIM];
     const float gSMf = gSM;
     const float gSLZa = gSLZ;
-    float gRech = gF[HBV_F_RECHARGE] + gRE;
-    float gExc = gF[HBV_F_EXCS] + gRE;
+    float gRech = cot_add<QO>(gF[HBV_F_RECHARGE], gRE);
+    float gExc = cot_add<QO>(gF[HBV_F_EXCS], gRE);
 
     // Capillary
     float gSM3, gSLZ_in;
@@ -394,7 +400,7 @@ __device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, con
         const float gb = (tp.SMc >= nz) ? gSMf : 0.f;     // SMf  = max(SM3 + cap*dt, nz)
         gSLZ_in = ga;
         gSM3 = gb;
-        const float gcap = gF[HBV_F_CAPILLARY] - D(ga) + D(gb);
+        const float gcap = QO ? D(gb) - D(ga) : gF[HBV_F_CAPILLARY] - D(ga) + D(gb);
         const float gc2 = ID(gcap);                       // capillary = c2/dt
         const float wL = min_w(tp.SLZin, tp.c1);          // c2 = min(SLZ, c1)
         gSLZ_in += gc2 * wL;
@@ -414,13 +420,13 @@ __device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, con
     // SM3 = max(SMd, nz) ; SMd = SM2 - ET*dt
     const float gd = (tp.SMd >= nz) ? gSM3 : 0.f;
     float gSM2 = gd;
-    const float gET = gF[HBV_F_AET] - D(gd);
+    const float gET = QO ? -D(gd) : gF[HBV_F_AET] - D(gd);
     // ET = et2/dt ; et2 = min(SM2, et1) ; et1 = PET*ef*dt
     const float get2 = ID(gET);
     const float wE = min_w(tp.SM2, tp.et1);
     gSM2 += get2 * wE;
     const float get0 = D(get2 * (1.f - wE));
-    const float gef = gF[HBV_F_EVAPFACTOR] + get0 * PET;
+    const float gef = QO ? get0 * PET : gF[HBV_F_EVAPFACTOR] + get0 * PET;
     gPET = get0 * tp.ef;                                   // d/dPET (as the step uses it)
     const float gef1 = (tp.ef1 >= 0.f && tp.ef1 <= 1.f) ? gef : 0.f;
     float gef0 = gef1;
@@ -483,7 +489,7 @@ __device__ __forceinline__ void soil_bwd(float& gSM, float& gSLZ, float gRE, con
 // snow_bwd: in  gSP (= dL/dSNOWPACK after the step, the SWE series' cotangent NOT yet added),
 //           gMW (after the step), gW (from soil_bwd), gF; out gSP, gMW before the step,
 //           gP = dL/dP, gT = dL/dT.
-template <int VAR>
+template <int VAR, bool QO = false>
 __device__ __forceinline__ void snow_bwd(float& gSP, float& gMW, float gW, const float (&gF)[HBV_MAX_FLUX],
                                          const float (&p)[Traits<VAR>::NPAR], const LaneConst& c,
                                          const Tape& tp, float (&gp)[Traits<VAR>::NPAR],
@@ -492,10 +498,10 @@ __device__ __forceinline__ void snow_bwd(float& gSP, float& gMW, float gW, const
     const float dt = c.dt, inv_dt = c.inv_dt;
     auto D = [&](float x) { return TR::HOURLY ? x * dt : x; };
     auto ID = [&](float x) { return TR::HOURLY ? x * inv_dt : x; };
-    float gSP3 = gSP + gF[HBV_F_SWE];
+    float gSP3 = cot_add<QO>(gF[HBV_F_SWE], gSP);
     const float gMW3 = gMW;
     // W = RAIN + tosoil ; MW3 = MW2 - tosoil*dt ; tosoil = max(ts0, 0) ; ts0 = (MW2 - CWH*SP3)/dt
-    const float gtosoil = gF[HBV_F_TOSOIL] + gW - D(gMW3);
+    const float gtosoil = QO ? gW - D(gMW3) : gF[HBV_F_TOSOIL] + gW - D(gMW3);
     const float gx = (tp.ts0 >= 0.f) ? ID(gtosoil) : 0.f;
     const float gMW2 = gMW3 + gx;
     gp[HBV_P_CWH] -= gx * tp.SP3;
@@ -534,15 +540,15 @@ __device__ __forceinline__ void snow_bwd(float& gSP, float& gMW, float gW, const
 // Adjoint step.  On entry gS = dL/d(state after the step); gF = dL/d(per-lane fluxes of the
 // step).  On exit gS = dL/d(state before the step), gp[i] += dL/d(parameter i at this step) and
 // gX = dL/d(P, T, PET) of this step as the step uses them (hourly: P, PET already / dt).
-template <int VAR, bool BETAET>
+template <int VAR, bool BETAET, bool QO = false>
 __device__ __forceinline__ void step_bwd(float (&gS)[5], const float (&gF)[HBV_MAX_FLUX],
                                          const float (&p)[Traits<VAR>::NPAR], float PET,
                                          const LaneConst& c, const Tape& tp,
                                          float (&gp)[Traits<VAR>::NPAR], float (&gX)[3]) {
     float gRE, gW;
-    resp_bwd<VAR>(gS[3], gS[4], gF, p, c, tp, gp, gRE);
-    soil_bwd<VAR, BETAET>(gS[2], gS[4], gRE, gF, p, PET, c, tp, gp, gW, gX[2]);
-    snow_bwd<VAR>(gS[0], gS[1], gW, gF, p, c, tp, gp, gX[0], gX[1]);
+    resp_bwd<VAR, QO>(gS[3], gS[4], gF, p, c, tp, gp, gRE);
+    soil_bwd<VAR, BETAET, QO>(gS[2], gS[4], gRE, gF, p, PET, c, tp, gp, gW, gX[2]);
+    snow_bwd<VAR, QO>(gS[0], gS[1], gW, gF, p, c, tp, gp, gX[0], gX[1]);
 }
 
 __device__ __forceinline__ void init_lane_const(LaneConst& lc, float Ac, float Elev) {
