@@ -184,9 +184,11 @@ hbv_fwd_pipe_kernel(const KDesc d, const FwdPtrs io) {
     const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
     const int kA = tid & 15, bbA = tid >> 4;
     const bool actA = kA < 3;
-    const float* srcA = io.forcing + (int64_t)min(b0w + bbA, d.B - 1) * 3 + kA;
+    // sources as (row-0 pointer, byte stride per step): one IMAD.WIDE.U32 per copy (hbv_lean.cu)
+    const char* const baseA = reinterpret_cast<const char*>(io.forcing + (int64_t)min(b0w + bbA, d.B - 1) * 3 + kA);
+    const uint32_t strA = (uint32_t)d.B * 12u, strB = (uint32_t)d.B * (uint32_t)d.dyn_ncol * 4u;
     const int dstA = 4 * bbA + kA;
-    const float* srcB[NB > 0 ? NB : 1];
+    const char* baseB[NB > 0 ? NB : 1];
     int dstB[NB > 0 ? NB : 1];
     bool actB[NB > 0 ? NB : 1];
 #pragma unroll
@@ -199,21 +201,18 @@ hbv_fwd_pipe_kernel(const KDesc d, const FwdPtrs io) {
 #pragma unroll
         for (int i = 0; i < NPAR; ++i)
             if (DS::is_dyn(i, 0) && DS::slot(i) == k) col = pipe_col<NPAR, DM, LAYOUT>(i);
-        srcB[o] = io.dyn + (int64_t)min(b0w + bb, d.B - 1) * d.dyn_ncol + col + 2 * q;
+        baseB[o] = reinterpret_cast<const char*>(io.dyn + (int64_t)min(b0w + bb, d.B - 1) * d.dyn_ncol + col + 2 * q);
         dstB[o] = PARB + k * 32 + bb * 16 + 2 * q;
     }
     int t_issue = 0;
     auto issue = [&](float* wp) {    // stage the next time step (the last row again past the end)
-        if (actA) cp_async4(wp + dstA, srcA);
+        const uint64_t ts = (uint32_t)t_issue;
+        if (actA) cp_async4(wp + dstA, reinterpret_cast<const float*>(baseA + ts * strA));
 #pragma unroll
         for (int o = 0; o < NB; ++o)
-            if (actB[o]) cp_async8(wp + dstB[o], srcB[o]);
+            if (actB[o]) cp_async8(wp + dstB[o], reinterpret_cast<const float*>(baseB[o] + ts * strB));
         cp_async_commit();
-        if (++t_issue < T) {
-            srcA += sf;
-#pragma unroll
-            for (int o = 0; o < NB; ++o) srcB[o] += sd;
-        }
+        if (t_issue + 1 < T) ++t_issue;
     };
 #pragma unroll 1
     for (int q = 0; q < RD - 1; ++q) issue(ring0 + q * SLOT);      // steps 0 .. RD-2
