@@ -107,8 +107,12 @@ extern "C" int hbv_b200_copy_cols(float* dst, const float* src, int64_t rows, in
                     row_stride % 2 == 0 && ncols % 2 == 0;
     const int vec = v4 ? 4 : (v2 ? 2 : 1);
     const int64_t n = rows * (ncols / vec);
+    // a grid-stride copy whose CTAs live as long as the copy: two blocks per SM keep ~1 MB of PCIe
+    // requests in flight (far beyond the link's bandwidth-delay product) and leave the SMs' other
+    // warp slots to the step's kernels and to the copy of the opposite direction
+    const int64_t per_sm = opt(OPT_COPY_BLOCKS) > 0 ? opt(OPT_COPY_BLOCKS) : 2;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec == 4)
         copy_cols_kernel<float4><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(d), reinterpret_cast<const float4*>(s),

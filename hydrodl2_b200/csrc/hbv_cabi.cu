@@ -16,7 +16,7 @@ static std::atomic<long long> g_pipe_launches{0};
 // option table: environment at first use, then hbv_b200_set_option
 static const char* const kOptNames[OPT_COUNT] = {
     "LEAN", "PIPE", "PIPE_MAX", "RING", "LEAN_SMALL", "LEAN_BWD_RING", "LEAN_DEEP", "DENSE", "DENSE_NS", "DENSE_NS_BWD",
-    "DENSE_MINB", "CKPT", "ADJ_BPB"};
+    "DENSE_MINB", "CKPT", "ADJ_BPB", "COPY_BLOCKS"};
 static std::atomic<long long> g_opt[OPT_COUNT];
 static std::atomic<int> g_opt_init{0};
 static void opt_init() {

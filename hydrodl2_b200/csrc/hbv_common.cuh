@@ -338,6 +338,7 @@ enum Opt {
     OPT_DENSE_NS, OPT_DENSE_NS_BWD, OPT_DENSE_MINB,
     OPT_CKPT,             // checkpoint interval hbv_b200_auto_ckpt returns (experiments)
     OPT_ADJ_BPB,          // basins per CTA of K3's forward (experiments; unset: by measurement)
+    OPT_COPY_BLOCKS,      // hbv_b200_copy_cols: 256-thread blocks per SM (unset: 2)
     OPT_COUNT
 };
 long long opt(Opt o);

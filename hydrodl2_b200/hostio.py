@@ -49,6 +49,11 @@ def _merge_blocks(blocks):
 # ran at the same 55 GB/s.  'auto' (default) therefore times both ways once per tensor and
 # direction on the caller's own buffers (`PipelinedSteps`, first step) and keeps the faster one; the
 # SM-driven copy has to win by 15 % to be taken, since it competes with the step's kernels.
+# Upload and download do not run at full duplex for these 64-byte pieces whatever the mix: both
+# directions at once take the SUM of their times (copy engine: 1.88 + 2.31 -> 3.77 ms; SM-driven:
+# 2.49 + 2.49 -> 5.07 ms; more copy streams change nothing — scripts/experiments/stage_split.py), and
+# the pipelined step measures 3.6 / 3.9 / 3.6 / 4.4 ms for (up, down) = (dma, dma) / (dma, kernel) /
+# (kernel, dma) / (kernel, kernel).
 BLOCK_COPY = os.environ.get('HBV_B200_BLOCK_COPY', 'auto')
 
 
@@ -91,10 +96,12 @@ def sparse_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cu
 
 
 def pick_block_copy(dst: torch.Tensor, src: torch.Tensor, fp: dict, stream: torch.cuda.Stream) -> str:
-    """'dma' or 'kernel' for this (tensor, direction, footprint): BLOCK_COPY when it names one,
-    else both timed on `stream` (one warm copy + one timed copy each; the copies are idempotent)."""
-    if BLOCK_COPY in ('dma', 'kernel'):
-        return BLOCK_COPY
+    """'dma' or 'kernel' for this (tensor, direction, footprint): BLOCK_COPY when it names one
+    ('dma', 'kernel', or 'up,down' e.g. 'dma,kernel'), else both timed on `stream` (one warm copy +
+    one timed copy each; the copies are idempotent)."""
+    forced = BLOCK_COPY.split(',')
+    if all(f in ('dma', 'kernel') for f in forced):
+        return forced[0] if dst.is_cuda or len(forced) == 1 else forced[1]
     if not fp.get('col_blocks'):
         return 'dma'
     ms = {}
