@@ -68,6 +68,9 @@ SEED = 20261017
 NO_ALLREDUCE = os.environ.get('HBV_BENCH_NO_ALLREDUCE') == '1'
 # capture the shared-gradient all-reduce inside the CUDA graph of the step (several GPUs)
 GRAPH_ALLREDUCE = os.environ.get('HBV_BENCH_GRAPH_ALLREDUCE', '0') == '1'
+# one-shot all-reduce on a parallel branch of the step's graph, one step behind (0: in line, at the
+# end of the step it belongs to)
+OVERLAP_ALLREDUCE = os.environ.get('HBV_BENCH_OVERLAP_ALLREDUCE', '1') == '1'
 
 
 # ----------------------------------------------------------------------------------------------
@@ -422,9 +425,12 @@ def run_b200(args):
         with torch.no_grad():
             return model({'x_phy': x}, p)
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, tail=None):
+        # tail: work that closes the K steps and belongs to them (the flush of a pipelined reduction)
         for _ in range(warmup):
             fn()
+        if tail:
+            tail()
         torch.cuda.synchronize(dev)
         D.barrier()
         torch.cuda.synchronize(dev)
@@ -434,6 +440,8 @@ def run_b200(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if tail:
+            tail()
         e1.record()
         torch.cuda.synchronize(dev)
         if sampler:
@@ -500,6 +508,7 @@ def run_b200(args):
     # the timed step: eager by default; --graph replays the same step from a CUDA graph
     graph_note = 'eager'
     step_fn = lambda: train_step(model, x_dev, p_dev)   # noqa: E731
+    step_tail = None
     if args.graph:
         try:
             from hydrodl2_b200.graphs import GraphedStep
@@ -507,6 +516,39 @@ def run_b200(args):
                 gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=False), warmup=3, device=dev)
                 step_fn = gstep.replay
                 graph_note = 'cuda graph replay of the whole step (hydrodl2_b200.graphs.GraphedStep)'
+            elif oneshot and not NO_ALLREDUCE and OVERLAP_ALLREDUCE:
+                # The collective is a plain kernel of this library, captured with the step — on a
+                # parallel branch of the graph: replay i reduces the shared gradient of step i-1
+                # (staged by replay i-1) while it computes step i, so the cross-rank wait of the
+                # reduction is off the step's critical path (rank skew up to one step is absorbed).
+                # Every step's gradient is still reduced, one step late; the last one by `tail`,
+                # inside the timed region.
+                n_sh = wl['n_par'] * NMUL + 2
+                stage = torch.zeros(n_sh, device=dev)        # step i-1's local shared gradient
+                reduced = torch.zeros(n_sh, device=dev)      # the latest finished reduction
+                comm = torch.cuda.Stream(dev)
+
+                def overlapped_step():
+                    cur = torch.cuda.current_stream(dev)
+                    comm.wait_stream(cur)
+                    with torch.cuda.stream(comm):
+                        reduced.copy_(stage)
+                        D.allreduce_shared_grad(reduced)
+                    out, loss, gsh = train_step(model, x_dev, p_dev, allreduce=False)
+                    cur.wait_stream(comm)
+                    stage.copy_(gsh)
+                    return out, loss, reduced
+
+                def flush_reduction():
+                    reduced.copy_(stage)
+                    D.allreduce_shared_grad(reduced)
+
+                gstep = GraphedStep(overlapped_step, warmup=3, device=dev)
+                step_fn, step_tail = gstep.replay, flush_reduction
+                graph_note = ('cuda graph replay of the whole step; the one-shot all-reduce of the shared gradient '
+                              '(csrc/allreduce.cu, NVLink peer memory) runs on a parallel branch of the graph, one '
+                              'step behind: replay i reduces step i-1\'s gradient while computing step i, the '
+                              'last one is flushed inside the timed region')
             elif oneshot and not NO_ALLREDUCE:
                 # the collective is a plain kernel of this library: captured with the step
                 gstep = GraphedStep(lambda: train_step(model, x_dev, p_dev, allreduce=True), warmup=3, device=dev)
@@ -535,8 +577,9 @@ def run_b200(args):
         except Exception as exc:   # pragma: no cover - depends on driver / NCCL
             graph_note = f'eager (graph capture failed: {type(exc).__name__}: {exc})'
             step_fn = lambda: train_step(model, x_dev, p_dev)   # noqa: E731
+            step_tail = None
             torch.cuda.synchronize(dev)
-    ms_step = timed(step_fn, args.steps, args.warmup, sampler) / args.steps
+    ms_step = timed(step_fn, args.steps, args.warmup, sampler, tail=step_tail) / args.steps
     value = world * B * T_MAIN / (ms_step * 1e-3)
     dom = max(kms, key=kms.get)
     roofline = roofline_of(wl, B, kms, dom, traffic_key=args.workload)
@@ -651,7 +694,9 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_of(wl, B, world),
             'run_info': {'ckpt_interval': k_eff(wl, B), 'launch': graph_note, 'eager_ms_per_step': ms_eager,
-                         'shared_grad_allreduce': ('one-shot kernel over NVLink peer memory' if oneshot else
+                         'shared_grad_allreduce': (('one-shot kernel over NVLink peer memory'
+                                                    + (', overlapped with the next step (one step behind)'
+                                                       if step_tail is not None else '')) if oneshot else
                                                    ('nccl' if world > 1 else 'none (one GPU)')),
                          'host_affinity': numa},
             'clocks': sampler.summary(), 'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
