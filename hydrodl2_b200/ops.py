@@ -157,11 +157,11 @@ def make_desc(spec: RunSpec, T: int, B: int, nvar: int, dyn_ncol: int, sta_ncol:
     d.nvar = nvar
     d.i_prcp, d.i_tmean, d.i_pet = spec.var_index
     d.dyn_ncol, d.sta_ncol = dyn_ncol, sta_ncol
-    for i in range(spec.n_par):
-        d.par_src[i] = spec.par_src[i]
-        d.par_col[i] = spec.par_col[i]
-        d.par_lo[i] = float(spec.par_lo[i])
-        d.par_hi[i] = float(spec.par_hi[i])
+    n = spec.n_par       # (slice assignment: one ctypes call per array, not one per element)
+    d.par_src[:n] = spec.par_src[:n]
+    d.par_col[:n] = spec.par_col[:n]
+    d.par_lo[:n] = [float(v) for v in spec.par_lo[:n]]
+    d.par_hi[:n] = [float(v) for v in spec.par_hi[:n]]
     d.nearzero = spec.nearzero
     d.dt = spec.dt
     d.ckpt_interval = spec.ckpt_interval
@@ -337,8 +337,9 @@ class _HbvRun(torch.autograd.Function):
         io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn_run), _ptr(sta)
         io.drop, io.attrs, io.muwts = _ptr(drop), _ptr(attrs), _ptr(mu)
         io.state_in, io.state_out = _ptr(state_in), _ptr(state_out)
+        flux0, plane = flux.data_ptr(), T * B * 4
         for f in range(spec.nflux):
-            io.flux[f] = flux[f].data_ptr()
+            io.flux[f] = flux0 + f * plane
         io.state_series, io.ckpt = _ptr(series), _ptr(ckpt)
         stream = _stream(dev)
         with torch.cuda.device(dev):
@@ -384,9 +385,10 @@ class _HbvRun(torch.autograd.Function):
         ctx.gbuf, ctx.gev, ctx.gfused = gbuf, gev, gfused
         ctx.save_for_backward(forcing, dyn, sta, drop, attrs, mu, ckpt, flux, uh, bfi_ws, state_in)
         ctx.set_materialize_grads(False)
-        outs = [flux[f] for f in range(spec.nflux)]
+        outs = list(flux.unbind(0)[:spec.nflux])
         n_r = spec.n_routed if spec.routing else 0
-        outs += [routed[s] for s in range(n_r)]
+        if n_r:
+            outs += list(routed.unbind(0)[:n_r])
         outs.append(bfi)        # None when routing / BFI is off
         outs.append(state_out)
         outs.append(series)     # None unless spec.state_series
