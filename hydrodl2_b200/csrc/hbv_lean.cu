@@ -124,8 +124,10 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
     // (t, state) planes are nlane apart.  A warp-major store [warp][t][state][32] — 640 contiguous
     // bytes per warp and step instead of five 128 B rows 4 nlane bytes apart — was measured at
-    // BASELINE config 4's per-GPU grid: K1s 8.02 -> 7.82 ms, K2s 12.29 -> 12.14 ms (with the stores
-    // kept in L2 altogether K1s takes 7.27 ms); not worth a second layout in every kernel family.
+    // BASELINE config 4's per-GPU grid: K1s 8.02 -> 7.82 ms, K2s 11.69 -> 11.30 ms, the step 21.27 ->
+    // 20.69 ms (with the stores kept in L2 altogether K1s takes 7.27 ms): 2.8 % of that step, against
+    // a second state layout in every kernel family (K1 / K2 are everyone's fallback) and in the
+    // `hbv_2` state-series alias — left for a next round.
     float* pk = CK ? io.ckpt + lane : nullptr;
 
     struct In { float P, T, E; float raw[ND]; };
