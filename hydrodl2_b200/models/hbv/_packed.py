@@ -20,7 +20,7 @@ from typing import Any, Optional, Union
 import torch
 
 from ... import _cabi as A
-from ...ops import RunSpec, hbv_run, hbv_states_only, start_grad_plane
+from ...ops import RunSpec, hbv_run, hbv_states_only, route_with_history, start_grad_plane
 from ._seam import PackedSeam
 
 _FLUX_KEYS = (
@@ -68,6 +68,12 @@ class PackedHbv(PackedSeam, torch.nn.Module):
         # K of the checkpointed adjoint (extension, not in reference): 0 = let the library pick
         # (every state for small problems, every 16th otherwise), or 1..64
         self.ckpt_interval = 0
+        # extension (not in the reference): with `cache_states`, also carry the last
+        # lenF - 1 steps of the un-routed series into the next call, so that the ROUTED flows of a
+        # run stepped chunk by chunk equal the one-shot run (in the reference — and here by
+        # default — the daily UH convolution restarts from an empty history at every call)
+        self.uh_carry_over = False
+        self._uh_hist = None
 
         self.states, self._states_cache = None, None
 
@@ -101,6 +107,7 @@ class PackedHbv(PackedSeam, torch.nn.Module):
             self.nmul = config.get('nmul', self.nmul)
             self.cache_states = config.get('cache_states', False)
             self.ckpt_interval = config.get('ckpt_interval', self.ckpt_interval)
+            self.uh_carry_over = config.get('uh_carry_over', self.uh_carry_over)
             if (not self._always_betaet) and 'parBETAET' in self.dynamic_params:
                 self.parameter_bounds['parBETAET'] = [0.3, 5]   # hbv.py:124-125
         self._set_parameters()
@@ -135,6 +142,7 @@ class PackedHbv(PackedSeam, torch.nn.Module):
         if not (isinstance(states, tuple) and len(states) == nstates):
             raise ValueError(f"`states` must be a tuple of {nstates} tensors.")
         self.states = tuple(s.detach().to(self.device, dtype=torch.float32) for s in states)
+        self._uh_hist = None         # a new starting point: no runoff history to route
 
     def _set_parameters(self) -> None:
         self.phy_param_names = self.parameter_bounds.keys()
@@ -215,6 +223,7 @@ class PackedHbv(PackedSeam, torch.nn.Module):
 
         if (not self.states) or (not self.cache_states):
             current = self._init_stack(ngrid)
+            self._uh_hist = None
         else:
             current = torch.stack(tuple(self.states))
 
@@ -236,6 +245,20 @@ class PackedHbv(PackedSeam, torch.nn.Module):
         drop = self._draw_drop(ngrid)
         res = hbv_run(spec, x[warm_up:], parameters, None, current, drop=drop,
                       muwts=self.muwts, t_off=warm_up, gplane=gplane)
+
+        if self.uh_carry_over and self.cache_states and self.routing:
+            # route [history of the previous calls ; this run] and keep this run's part
+            if torch.is_grad_enabled() and parameters.requires_grad:
+                raise RuntimeError('uh_carry_over is a streaming-inference option: call the model under '
+                                   'torch.no_grad() (the routed history of earlier calls carries no gradient)')
+            n_phy = len(self.parameter_bounds) * self.nmul
+            q_run = torch.stack([res['flux'][f] for f in _R2F]).detach()
+            hist = self._uh_hist
+            if hist is not None and hist.shape[2] != ngrid:
+                hist = None
+            routed, self._uh_hist = route_with_history(
+                spec, parameters[parameters.shape[0] - 1, :, n_phy:].detach(), parameters.shape[-1], q_run, hist)
+            res['routed'] = [routed[i] for i in range(routed.shape[0])]
 
         states = tuple(res['state_out'][i] for i in range(5))
         self._states_cache = [s.detach() for s in states]

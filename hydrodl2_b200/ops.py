@@ -542,6 +542,38 @@ def hbv_run(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs=None, m
     }
 
 
+def route_with_history(spec: RunSpec, route_t: torch.Tensor, route_stride: int, q_run: torch.Tensor,
+                       hist: Optional[torch.Tensor]):
+    """Streaming inference: gamma-UH routing (K4) of the run's un-routed series
+    `q_run` [n_routed, T, B] preceded by `hist` [n_routed, H, B], the last H <= lenF - 1 steps of
+    the previous calls — so a series routed chunk by chunk equals the one-shot routing.  No
+    gradient (raises under autograd).  Returns (routed [n_routed, T, B], new history)."""
+    if torch.is_grad_enabled() and (q_run.requires_grad or route_t.requires_grad):
+        raise RuntimeError('hydrodl2_b200: the UH history carry-over is an inference feature (use torch.no_grad())')
+    lib = A.load()
+    dev = q_run.device
+    n_r, T, B = q_run.shape
+    keep = max(spec.lenF - 1, 0)
+    if hist is None:
+        # "before the start" is zero flow: the window is always at least lenF long, so the unit
+        # hydrograph is built over all lenF taps as in a one-shot run of >= lenF steps (the
+        # reference normalises over min(lenF, T) taps, uh_routing.py:5-22)
+        hist = q_run.new_zeros((n_r, keep, B))
+    H = hist.shape[1]
+    q_cat = q_run.contiguous() if H == 0 else torch.cat([hist, q_run], dim=1).contiguous()
+    Tc = H + T
+    rdesc = make_route_desc(spec, Tc, B, route_stride)
+    rdesc.nser = n_r
+    routed = torch.empty((n_r, Tc, B), device=dev, dtype=torch.float32)
+    uh = torch.empty((min(spec.lenF, Tc), B), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        with _timed('route_fwd', dev):
+            A.check(lib.hbv_b200_route_fwd(C.byref(rdesc), route_t.data_ptr(), q_cat.data_ptr(), Tc * B,
+                                           routed.data_ptr(), Tc * B, uh.data_ptr(), None, None, _stream(dev)),
+                    'route_fwd')
+    return routed[:, H:], (q_cat[:, -keep:].clone() if keep > 0 else None)
+
+
 # ----------------------------------------------------------------------------------------------
 # K3: implicit HBV (`HbvAdj`, models/hbv/hbv_adj.py)
 # ----------------------------------------------------------------------------------------------

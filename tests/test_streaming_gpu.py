@@ -92,3 +92,44 @@ def test_hourly_qs_buffer_streaming_matches_oracle_routing():
         lo = max(0, t + 1 - m._max_history)
         ref = O.distr_routing(qs_cpu[lo:t + 1], distr, topo, areas, lenF=v.lenF)[-1:]
         assert_close(flow_steps[t], ref, RTOL_FLUX, f'hourly stepping: routed flow at step {t} (history {t + 1 - lo})')
+
+
+ROUTED = ['streamflow', 'srflow', 'ssflow', 'gwflow']
+
+
+@pytest.mark.parametrize('chunk', [30, 7, 1])
+def test_uh_carry_over_makes_chunked_routing_equal_one_shot(chunk):
+    """Extension of SURVEY f2 (`uh_carry_over`, off by default): with the last lenF - 1 steps of
+    un-routed flow carried from call to call, the ROUTED series of a run stepped chunk by chunk
+    equal the one-shot run — chunks longer than, shorter than, and much shorter than the 15-tap
+    unit hydrograph.  Without the option they do not (the reference's behaviour)."""
+    import hydrodl2_b200 as hydrodl2
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, B, nmul = 60, 13, 16
+    dyn = ['parBETA', 'parBETAET']
+    x = O.synthetic_forcing(T, B, seed=81).to(dev)
+    g = torch.Generator().manual_seed(82)
+    p = torch.randn(1, B, 13 * nmul + 2, generator=g).repeat(T, 1, 1)
+    for i in (0, 12):
+        p[:, :, i * nmul:(i + 1) * nmul] = torch.randn(T, B, nmul, generator=g)
+    p = p.to(dev)
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    cfg = {'warm_up': 0, 'dynamic_params': {'Hbv': dyn}, 'nmul': nmul}
+    with torch.no_grad():
+        one = M(cfg, device=dev)({'x_phy': x}, p)
+        m = M(dict(cfg, cache_states=True, uh_carry_over=True), device=dev)
+        parts = [m({'x_phy': x[t0:t0 + chunk].contiguous()}, p[t0:t0 + chunk].contiguous()) for t0 in range(0, T, chunk)]
+        plain = M(dict(cfg, cache_states=True), device=dev)
+        parts0 = [plain({'x_phy': x[t0:t0 + chunk].contiguous()}, p[t0:t0 + chunk].contiguous()) for t0 in range(0, T, chunk)]
+    for k in ROUTED + UNROUTED:
+        got = torch.cat([q[k] for q in parts], dim=0)
+        assert_close(got, one[k], RTOL_FLUX, f'uh_carry_over, chunk {chunk}: {k}', floor=STATE_FLOOR)
+    if chunk < T:
+        got0 = torch.cat([q['streamflow'] for q in parts0], dim=0)
+        assert float((got0 - one['streamflow']).abs().max()) > 1e-3 * float(one['streamflow'].abs().max())
+    # a new starting point clears the history; training is refused
+    m.load_states(tuple(m.get_states()))
+    assert m._uh_hist is None
+    with pytest.raises(RuntimeError, match='streaming-inference'):
+        m({'x_phy': x[:5].contiguous()}, p[:5].contiguous().requires_grad_(True))
