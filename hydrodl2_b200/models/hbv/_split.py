@@ -71,6 +71,10 @@ class SplitHbv(SplitSeam, torch.nn.Module):
         self.state_series = True
 
         self.states, self._state_cache, self._states_cache = None, None, None
+        # extension (see _packed.py): carry the runoff history of the fused <= 16-tap UH
+        # routing across `cache_states` calls (the hourly model keeps its own `_qs_buffer`)
+        self.uh_carry_over = False
+        self._uh_hist = None
 
         self.state_names = ['SNOWPACK', 'MELTWATER', 'SM', 'SUZ', 'SLZ']
         self.flux_names = [
@@ -95,6 +99,7 @@ class SplitHbv(SplitSeam, torch.nn.Module):
             self.nearzero = config.get('nearzero', self.nearzero)
             self.nmul = config.get('nmul', self.nmul)
             self.cache_states = config.get('cache_states', self.cache_states)
+            self.uh_carry_over = config.get('uh_carry_over', self.uh_carry_over)
             self.ckpt_interval = config.get('ckpt_interval', self.ckpt_interval)
             self.state_series = config.get('state_series', self.state_series)
         self._set_parameters()
@@ -120,6 +125,7 @@ class SplitHbv(SplitSeam, torch.nn.Module):
         if not (isinstance(states, tuple) and len(states) == nstates):
             raise ValueError(f"`states` must be a tuple of {nstates} tensors.")
         self.states = tuple(s.detach().to(self.device, dtype=torch.float32) for s in states)
+        self._uh_hist = None
 
     def _set_parameters(self) -> None:
         self.phy_param_names = self.parameter_bounds.keys()
@@ -191,6 +197,7 @@ class SplitHbv(SplitSeam, torch.nn.Module):
             current = torch.stack(tuple(states))
         elif (not self.states) or (not self.cache_states):
             current = torch.stack(self._init_states(ngrid))
+            self._uh_hist = None
         else:
             current = torch.stack(tuple(self.states))
         return x, dyn, sta, current, ngrid
@@ -222,6 +229,19 @@ class SplitHbv(SplitSeam, torch.nn.Module):
                                       sta.detach().contiguous(), current, drop=drop, attrs=attrs)
             return {'flux': None, 'routed': None, 'bfi': None, 'state_out': out, 'series': None}
         res = hbv_run(spec, x, dyn, sta, current, drop=drop, attrs=attrs, muwts=self.muwts)
+        if (self.uh_carry_over and self.cache_states and spec.routing
+                and self._variant != A.VARIANT_HOURLY):
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (dyn, sta)):
+                raise RuntimeError('uh_carry_over is a streaming-inference option: call the model under '
+                                   'torch.no_grad() (the routed history of earlier calls carries no gradient)')
+            from ...ops import route_with_history
+            rc = self._route_col()
+            q_run = torch.stack([res['flux'][f] for f in (A.F_QSIM, A.F_Q0, A.F_Q1, A.F_Q2)]).detach()
+            hist = self._uh_hist
+            if hist is not None and hist.shape[2] != x.shape[1]:
+                hist = None
+            routed, self._uh_hist = route_with_history(spec, sta.detach()[:, rc:], sta.shape[-1], q_run, hist)
+            res['routed'] = [routed[i] for i in range(routed.shape[0])]
         if long_uh:
             rc = self._route_col()
             self._apply_long_uh(res, x.shape[0], sta[:, rc:rc + 2],

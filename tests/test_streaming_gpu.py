@@ -133,3 +133,28 @@ def test_uh_carry_over_makes_chunked_routing_equal_one_shot(chunk):
     assert m._uh_hist is None
     with pytest.raises(RuntimeError, match='streaming-inference'):
         m({'x_phy': x[:5].contiguous()}, p[:5].contiguous().requires_grad_(True))
+
+
+def test_uh_carry_over_hbv_2():
+    """The same extension for the split daily model (`hbv_2`: routing parameters in the static
+    tensor)."""
+    import hydrodl2_b200 as hydrodl2
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, B, nmul, chunk = 48, 9, 16, 5
+    dyn = ['parBETA', 'parK0', 'parBETAET']
+    g = torch.Generator().manual_seed(91)
+    x = O.synthetic_forcing(T, B, seed=92).to(dev)
+    p0 = torch.rand(T, B, 3 * nmul, generator=g).to(dev)
+    p1 = torch.rand(B, 13 * nmul + 2, generator=g).to(dev)
+    xd = {'ac_all': (torch.rand(B, generator=g) * 5000).to(dev), 'elev_all': (torch.rand(B, generator=g) * 3500).to(dev)}
+    M = hydrodl2.load_model('hbv_2', ver_name='Hbv_2')
+    cfg = {'warm_up': 0, 'dynamic_params': {'Hbv_2': dyn}, 'nmul': nmul, 'routing': True}
+    with torch.no_grad():
+        one = M(cfg, device=dev)(dict(xd, x_phy=x), [p0, p1])
+        m = M(dict(cfg, cache_states=True, uh_carry_over=True), device=dev)
+        parts = [m(dict(xd, x_phy=x[t0:t0 + chunk].contiguous()), [p0[t0:t0 + chunk].contiguous(), p1])
+                 for t0 in range(0, T, chunk)]
+    for k in ROUTED:
+        got = torch.cat([q[k] for q in parts], dim=0)
+        assert_close(got, one[k], RTOL_FLUX, f'hbv_2 uh_carry_over: {k}', floor=STATE_FLOOR)
