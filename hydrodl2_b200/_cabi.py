@@ -34,7 +34,7 @@ class HbvDesc(C.Structure):
         ('par_col', C.c_int32 * HBV_MAX_PAR), ('par_lo', C.c_float * HBV_MAX_PAR),
         ('par_hi', C.c_float * HBV_MAX_PAR), ('nearzero', C.c_float), ('dt', C.c_float),
         ('ckpt_interval', C.c_int32), ('muwts_t_stride', C.c_int32), ('adj_max_updates', C.c_int32),
-        ('adj_tol', C.c_float), ('reserved', C.c_int32 * 4),
+        ('adj_tol', C.c_float), ('ckpt_layout', C.c_int32), ('reserved', C.c_int32 * 3),
     ]
 
 

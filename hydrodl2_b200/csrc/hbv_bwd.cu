@@ -61,6 +61,7 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
     const int b = valid ? b_raw : d.B - 1;
     const int64_t lane = (int64_t)b * nmul + j;
     const int64_t nlane = (int64_t)d.B * nmul;
+    const int64_t ckb = ck_base(d, lane), ckp = ck_plane(d);      // stored-state layout (hbv_common.cuh)
 
     LaneConst lc;
     lc.nearzero = d.nearzero; lc.dt = d.dt; lc.inv_dt = d.inv_dt;
@@ -252,9 +253,9 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
                                       dynmask, wp);
             if (isB && only_q) cp_async4(wp + GQ, gq_lane + (int64_t)t * d.B);
             if (K == 1) {       // every state was stored: stage the state before step t as well
-                const float* ck = io.ckpt + (int64_t)t * 5 * nlane + lane;
+                const float* ck = io.ckpt + ckb + (int64_t)t * 5 * ckp;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) cp_async4(wp + CK + s, ck + s * nlane);
+                for (int s = 0; s < 5; ++s) cp_async4(wp + CK + s, ck + s * ckp);
             }
         }
         wp += step_floats;
@@ -285,9 +286,9 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
             for (int q = 0; q < GQ; ++q) nxt.v[q] = tmp.v[q];
             if (isB && only_q) nxt.v[GQ] = __ldg(gq_lane + (int64_t)t * d.B);
             if (K == 1) {
-                const float* ck = io.ckpt + (int64_t)t * 5 * nlane + lane;
+                const float* ck = io.ckpt + ckb + (int64_t)t * 5 * ckp;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) nxt.v[CK + s] = __ldg(ck + s * nlane);
+                for (int s = 0; s < 5; ++s) nxt.v[CK + s] = __ldg(ck + s * ckp);
             }
         }
     };
@@ -345,9 +346,9 @@ hbv_bwd_kernel(const KDesc d, const BwdPtrs io) {
         const int len = min(d.T - t0, K);
         float S[5];
         {
-            const float* ck = io.ckpt + (int64_t)seg * 5 * nlane + lane;
+            const float* ck = io.ckpt + ckb + (int64_t)seg * 5 * ckp;
 #pragma unroll
-            for (int s = 0; s < 5; ++s) S[s] = __ldg(ck + s * nlane);
+            for (int s = 0; s < 5; ++s) S[s] = __ldg(ck + s * ckp);
         }
         // ---- pass A: recompute the segment, push the state before every step ---------------
         float* st = my_stack;

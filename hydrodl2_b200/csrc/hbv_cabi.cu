@@ -16,7 +16,7 @@ static std::atomic<long long> g_pipe_launches{0};
 // option table: environment at first use, then hbv_b200_set_option
 static const char* const kOptNames[OPT_COUNT] = {
     "LEAN", "PIPE", "PIPE_MAX", "RING", "LEAN_SMALL", "LEAN_BWD_RING", "LEAN_DEEP", "DENSE", "DENSE_NS", "DENSE_NS_BWD",
-    "DENSE_MINB", "CKPT", "ADJ_BPB", "COPY_BLOCKS"};
+    "DENSE_MINB", "CKPT", "ADJ_BPB", "COPY_BLOCKS", "CKPT_LAYOUT"};
 static std::atomic<long long> g_opt[OPT_COUNT];
 static std::atomic<int> g_opt_init{0};
 static void opt_init() {
@@ -101,6 +101,8 @@ int make_kdesc(const hbv_desc_t* s, KDesc& d) {
     d.nvar = s->nvar; d.i_prcp = s->i_prcp; d.i_tmean = s->i_tmean; d.i_pet = s->i_pet;
     d.dyn_ncol = s->dyn_ncol; d.sta_ncol = s->sta_ncol; d.apply_sigmoid = s->apply_sigmoid;
     d.K = s->ckpt_interval; d.muwts_t_stride = s->muwts_t_stride;
+    if (s->ckpt_layout != 0 && s->ckpt_layout != 1) { set_error("ckpt_layout must be 0 or 1"); return HBV_E_CKPT; }
+    d.ck_layout = s->ckpt_layout;
     d.nearzero = s->nearzero; d.dt = s->dt; d.inv_dt = 1.0f / s->dt;
     d.BPB = choose_bpb(s->B, s->nmul);
     for (int i = 0; i < np; ++i) {
@@ -177,7 +179,10 @@ int64_t hbv_b200_workspace_bytes(const hbv_desc_t* desc) {
     if (desc->ckpt_interval < 0) { hbv::set_error("negative ckpt_interval"); return HBV_E_CKPT; }
     const int K = desc->ckpt_interval > 0 ? desc->ckpt_interval : hbv_b200_auto_ckpt(desc->T, desc->B, desc->nmul);
     const int64_t nseg = ((int64_t)desc->T + K - 1) / K;
-    return nseg * 5 * (int64_t)desc->B * desc->nmul * (int64_t)sizeof(float);
+    const int64_t nlane = (int64_t)desc->B * desc->nmul;
+    // warp-major layout: whole 32-lane groups
+    const int64_t lanes = desc->ckpt_layout == 1 ? (nlane + 31) / 32 * 32 : nlane;
+    return nseg * 5 * lanes * (int64_t)sizeof(float);
 }
 
 int hbv_b200_fwd(const hbv_desc_t* desc, const hbv_fwd_io_t* io, void* stream) {

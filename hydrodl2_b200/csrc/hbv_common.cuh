@@ -16,6 +16,8 @@ struct KDesc {
     int dyn_ncol, sta_ncol;
     int apply_sigmoid;
     int K;               // checkpoint interval
+    int ck_layout;       // stored states: 0 = planes [segment][5][lane]; 1 = warp-major
+                         // [lane / 32][segment][5][32] (hbv_desc_t.ckpt_layout)
     int muwts_t_stride;
     int BPB;             // basins per CTA
     int nstage;          // input ring: cp.async groups in flight + 1 (2..4); hbv_dense.cu: ring slots
@@ -27,6 +29,19 @@ struct KDesc {
     float lo[HBV_MAX_PAR];
     float span[HBV_MAX_PAR];  // hi - lo
 };
+
+// Stored-state addressing (floats): state s of segment g for global lane L sits at
+//   ck_base(d, L) + (g * 5 + s) * ck_plane(d).
+// Layout 1 gives a warp ONE contiguous 640 B run per stored step (and consecutive steps adjacent)
+// instead of five 128 B rows 4 * nlane bytes apart: measured on BASELINE config 4's per-GPU grid,
+// K1s 8.02 -> 7.82 ms and K2s 11.69 -> 11.30 ms.
+__host__ __device__ __forceinline__ int64_t ck_nseg(const KDesc& d) { return d.K > 0 ? (d.T + d.K - 1) / d.K : 0; }
+__host__ __device__ __forceinline__ int64_t ck_plane(const KDesc& d) {
+    return d.ck_layout ? 32 : (int64_t)d.B * d.nmul;
+}
+__host__ __device__ __forceinline__ int64_t ck_base(const KDesc& d, int64_t lane) {
+    return d.ck_layout ? (lane >> 5) * (ck_nseg(d) * 5 * 32) + (lane & 31) : lane;
+}
 
 struct FwdPtrs {
     const float* forcing; const float* dyn; const float* sta; const uint8_t* drop;
@@ -339,6 +354,7 @@ enum Opt {
     OPT_CKPT,             // checkpoint interval hbv_b200_auto_ckpt returns (experiments)
     OPT_ADJ_BPB,          // basins per CTA of K3's forward (experiments; unset: by measurement)
     OPT_COPY_BLOCKS,      // hbv_b200_copy_cols: 256-thread blocks per SM (unset: 2)
+    OPT_CKPT_LAYOUT,      // read by the host side (ops.py): 0 / 1 force the stored-state layout (unset: policy)
     OPT_COUNT
 };
 long long opt(Opt o);

@@ -643,6 +643,7 @@ template <int VAR, bool BETAET, int DM>
 int try_fwd_dense(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream_t st) {
     constexpr int NPAR = Traits<VAR>::NPAR;
     if (!write_flux || io.drop != nullptr || !dense_shape_ok(d, DM)) return HBV_NOT_ELIGIBLE;
+    if (d.ck_layout != 0 && io.ckpt != nullptr) return HBV_NOT_ELIGIBLE;      // (bulk copies of CTA-wide state rows: plane layout only)
     if (layout_matches<NPAR, DM, 0>(d)) return launch_fwd_dense<VAR, BETAET, DM, 0>(d, io, st);
     if (layout_matches<NPAR, DM, 1>(d)) return launch_fwd_dense<VAR, BETAET, DM, 1>(d, io, st);
     return HBV_NOT_ELIGIBLE;
@@ -653,7 +654,7 @@ int try_fwd_dense(const KDesc& d, const FwdPtrs& io, bool write_flux, cudaStream
 template <int VAR, bool BETAET, int DM>
 int try_bwd_dense(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     constexpr int NPAR = Traits<VAR>::NPAR;
-    if (d.K != 1 || io.drop != nullptr || io.gdyn == nullptr || !dense_shape_ok(d, DM)) return HBV_NOT_ELIGIBLE;
+    if (d.K != 1 || d.ck_layout != 0 || io.drop != nullptr || io.gdyn == nullptr || !dense_shape_ok(d, DM)) return HBV_NOT_ELIGIBLE;
     if (reinterpret_cast<uintptr_t>(io.ckpt) % 16 != 0) return HBV_NOT_ELIGIBLE;
     if (((long long)d.B * d.dyn_ncol) % 4 != 0) return HBV_NOT_ELIGIBLE;
     if (layout_matches<NPAR, DM, 0>(d)) return launch_bwd_dense<VAR, BETAET, DM, 0>(d, io, st);

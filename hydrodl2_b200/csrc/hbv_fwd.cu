@@ -141,16 +141,17 @@ hbv_fwd_kernel(const KDesc d, const FwdPtrs io) {
     }
 
     int ck_next = (d.K > 0 && io.ckpt != nullptr) ? 0 : 0x7fffffff;
-    float* ck_ptr = io.ckpt ? io.ckpt + lane : nullptr;
+    float* ck_ptr = io.ckpt ? io.ckpt + ck_base(d, lane) : nullptr;     // (layout: hbv_common.cuh)
+    const int64_t ckp = ck_plane(d);
 
     Tape tp;
     auto do_step = [&](const auto& in, int t, int tc) {
         if (t == ck_next) {
             if (valid) {
 #pragma unroll
-                for (int s = 0; s < 5; ++s) ck_ptr[s * nlane] = S[s];
+                for (int s = 0; s < 5; ++s) ck_ptr[s * ckp] = S[s];
             }
-            ck_ptr += 5 * nlane;
+            ck_ptr += 5 * ckp;
             ck_next += d.K;
         }
         ring_apply_dyn<NPAR, DM>(d, dynmask, in, p, nullptr);

@@ -83,7 +83,11 @@ __device__ __forceinline__ void lean_descale_both(int i, float raw, float span, 
 // the first use of the oldest buffer also waits for the loads issued a moment ago — ncu attributed
 // 28 % of the kernel's stall samples to that single wait on BASELINE config 4's per-GPU grid
 // (2.1 warps per scheduler).  cp.async groups complete in FIFO order and are waited for by count.
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true, int KS = 1>
+// CKL: layout of the state store (hbv_common.cuh) as a compile-time fact — warp-major puts the five
+// states of a stored step at immediate offsets from one pointer (10 instructions per step less than
+// five planes a runtime stride apart); compiled for the chunk-ring form with KS 1 / 4 only
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, bool CK, int LBPB, int RD, bool WF = true, int KS = 1,
+          int CKL = 0>
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? (RD < 0 ? 4 : 6) : 1)
 hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     static_assert(LTC % KS == 0, "checkpoint interval must divide the output chunk");
@@ -122,13 +126,11 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
     const float* pf = io.forcing + (int64_t)b * 3;
     const float* pd = io.dyn + (int64_t)b * d.dyn_ncol + j;
     const int64_t sf = (int64_t)d.B * 3, sd = (int64_t)d.B * d.dyn_ncol;
-    // (t, state) planes are nlane apart.  A warp-major store [warp][t][state][32] — 640 contiguous
-    // bytes per warp and step instead of five 128 B rows 4 nlane bytes apart — was measured at
-    // BASELINE config 4's per-GPU grid: K1s 8.02 -> 7.82 ms, K2s 11.69 -> 11.30 ms, the step 21.27 ->
-    // 20.69 ms (with the stores kept in L2 altogether K1s takes 7.27 ms): 2.8 % of that step, against
-    // a second state layout in every kernel family (K1 / K2 are everyone's fallback) and in the
-    // `hbv_2` state-series alias — left for a next round.
-    float* pk = CK ? io.ckpt + lane : nullptr;
+    // consecutive (segment, state) planes are ck_plane apart in either layout of the store
+    // (hbv_common.cuh: planes over all lanes, or warp-major — 640 contiguous bytes per warp and
+    // stored step; with the stores kept in L2 altogether this kernel takes 7.27 instead of 8.02 ms
+    // on BASELINE config 4's per-GPU grid, with the warp-major layout 7.82)
+    float* pk = CK ? io.ckpt + (CKL ? (lane >> 5) * (ck_nseg(d) * 160) + (lane & 31) : lane) : nullptr;
 
     struct In { float P, T, E; float raw[ND]; };
     int t_issue = 0;
@@ -161,7 +163,11 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
         if constexpr (CK) {
             if (tc % KS == 0) {        // (tc is a literal at every call site)
 #pragma unroll
-                for (int s = 0; s < 5; ++s) { if (valid) *pk = S[s]; pk += nlane; }
+                for (int s = 0; s < 5; ++s) {
+                    if constexpr (CKL) { if (valid) pk[s * 32] = S[s]; }
+                    else { if (valid) *pk = S[s]; pk += nlane; }
+                }
+                if constexpr (CKL) pk += 160;
             }
         }
 #pragma unroll
@@ -340,7 +346,8 @@ hbv_fwd_lean_kernel(const KDesc d, const FwdPtrs io) {
 // KS-1 missing states are recomputed from the stored one and kept in registers, and the KS steps
 // are swept in reverse — one extra tape-free forward step per missing state instead of 320 B of
 // state traffic per basin-step written by the forward and read back here.
-template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false, int KS = 1>
+template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG, int LBPB, int PF, int RD, bool ZF = false, int KS = 1,
+          int CKL = 0>      // CKL: as in the forward kernel (ring form, KS 1 / 4)
 // (one-warp form: registers unconstrained — 17 resident warps per SM; forcing 20-28 was measured
 // equal or slower on the 22.5k-basin shard, 4.31 / 5.55 / 5.72 ms: the kernel is HBM-bound there)
 __global__ void __launch_bounds__(LBPB * LNM, LBPB == 8 ? 4 : 1)
@@ -384,6 +391,7 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     const float* pf = io.forcing + row_last * 3;
     const float* pd = io.dyn + row_last * d.dyn_ncol + j;
     const float* pq = io.gflux[HBV_F_QSIM] + row_last;
+    static_assert(CKL == 0 || (RD > 0 && LBPB == 2), "warp-major state store: ring form only");
     const float* pc = io.ckpt + (int64_t)d.T * 5 * nlane + lane;     // one plane past (T-1, state 4)
     float* pg = io.gdyn + row_last * d.dyn_ncol + j;
     constexpr float inv_nmul = 1.0f / (float)LNM;
@@ -445,11 +453,14 @@ hbv_bwd_lean_kernel(const KDesc d, const BwdPtrs io) {
     const bool actC = 4 * qC < 16 * nbw;
     // stored states: plane (segment, state) at ckpt + (5 segment + state) nlane, segment = t / KS
     const int64_t seg_last = (d.T - 1) / KS;
-    const float* srcC = io.ckpt + (seg_last * 5 + sC) * nlane + (int64_t)b0w * LNM + 4 * qC;
-    const float* srcD = io.ckpt + (seg_last * 5 + 4) * nlane + (int64_t)b0w * LNM + 4 * qC;
+    // (warp-major store: a one-warp CTA's 32 lanes are one 32-lane group, b0w * LNM = 32 * blockIdx.x)
+    const int64_t ckw = CKL ? (int64_t)blockIdx.x * (ck_nseg(d) * 160) : (int64_t)b0w * LNM;
+    const int64_t ckp = CKL ? 32 : nlane;
+    const float* srcC = io.ckpt + ckw + (seg_last * 5 + sC) * ckp + 4 * qC;
+    const float* srcD = io.ckpt + ckw + (seg_last * 5 + 4) * ckp + 4 * qC;
     const bool actD = actC && tid < 8;
     const int dstC = STB + sC * 32 + 4 * qC, dstD = STB + 4 * 32 + 4 * qC;
-    const int64_t strC = 5 * nlane;
+    const int64_t strC = CKL ? 160 : 5 * nlane;
     int t_stage = d.T - 1;
     auto issue = [&]() {             // stage the inputs of the next step of the sweep (if any)
         if (t_stage >= 0) {
@@ -690,6 +701,17 @@ static int launch_fwd_lean_b(KDesc d, const FwdPtrs& io, cudaStream_t st) {
     constexpr int slots = RD > 0 ? RD : (RD < 0 ? LNCH * LTC : 0);
     constexpr size_t smem = ((size_t)LTC * LBPB * (LNM * NFP + 12) + (size_t)slots * (4 * LBPB + LBPB * LNM * ND)) * sizeof(float);
     const int grid = (d.B + LBPB - 1) / LBPB;
+    if constexpr (LBPB == 8 && RD < 0) {
+        if (io.ckpt != nullptr && d.ck_layout == 1) {      // (try_fwd_lean let in K = 1 / 4 only)
+            if (d.K == 1) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 1, 1>, smem>(grid, LBPB * LNM, st, d, io);
+            else lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 4, 1>, smem>(grid, LBPB * LNM, st, d, io);
+            count_launch();
+            count_lean_launch();
+            cudaError_t e1 = cudaGetLastError();
+            if (e1 != cudaSuccess) set_error(cudaGetErrorString(e1));
+            return (int)e1;
+        }
+    }
     if (io.ckpt == nullptr) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, false, LBPB, RD>, smem>(grid, LBPB * LNM, st, d, io);
     else if (d.K == 1) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD>, smem>(grid, LBPB * LNM, st, d, io);
     else if (d.K == 2) lean_go<hbv_fwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, true, LBPB, RD, true, 2>, smem>(grid, LBPB * LNM, st, d, io);
@@ -726,7 +748,14 @@ int try_fwd_lean_warm(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
 
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
-    if (lean_small_grid(d, io.ckpt != nullptr)) return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
+    // the warp-major state store is compiled for the chunk-ring form with K = 1 / 4 (hbv_common.cuh;
+    // what the host-side policy asks for); anything else with that layout takes K1
+    const bool wm = io.ckpt != nullptr && d.ck_layout != 0;
+    if (wm && d.K != 1 && d.K != 4) return HBV_NOT_ELIGIBLE;
+    if (lean_small_grid(d, io.ckpt != nullptr)) {
+        if (wm) return HBV_NOT_ELIGIBLE;
+        return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, LRD_F>(d, io, st);
+    }
     // 128-thread CTAs: inputs through the chunk ring (cp.async, 8 B copies of the parameter runs)
     // up to `lean_deep` lanes, register prefetch above / when the rows are not 8 B aligned
     const long long deep_max = opt(OPT_LEAN_DEEP) >= 0 ? opt(OPT_LEAN_DEEP) : (1LL << 62);
@@ -736,6 +765,7 @@ static int launch_fwd_lean(const KDesc& d, const FwdPtrs& io, cudaStream_t st) {
     // hourly grid — step 24.1 / 22.7 / 22.4 ms — and equal within noise on the `hbv` ones.)
     if ((long long)d.B * LNM <= deep_max && d.dyn_ncol % 2 == 0 && reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0)
         return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, -1>(d, io, st);
+    if (io.ckpt != nullptr && d.ck_layout != 0) return HBV_NOT_ELIGIBLE;
     return launch_fwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 0>(d, io, st);
 }
 
@@ -747,7 +777,15 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
     const int grid = (d.B + LBPB - 1) / LBPB;
     if constexpr (LBPB == 2) {
         const bool zf = io.zero_fill && popc_c((unsigned)DM) * LNM != d.dyn_ncol;
-        if (d.K == 1) {
+        if (d.ck_layout == 1) {          // (try_bwd_lean let in K = 1 / 4 only)
+            if (d.K == 1) {
+                if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true, 1, 1><<<grid, LBPB * LNM, smem, st>>>(d, io);
+                else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false, 1, 1><<<grid, LBPB * LNM, smem, st>>>(d, io);
+            } else {
+                if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true, 4, 1><<<grid, LBPB * LNM, smem, st>>>(d, io);
+                else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false, 4, 1><<<grid, LBPB * LNM, smem, st>>>(d, io);
+            }
+        } else if (d.K == 1) {
             if (zf) hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, true><<<grid, LBPB * LNM, smem, st>>>(d, io);
             else hbv_bwd_lean_kernel<VAR, BETAET, DM, LAYOUT, SIG, LBPB, PF, RD, false><<<grid, LBPB * LNM, smem, st>>>(d, io);
         } else if (d.K == 2) {
@@ -770,8 +808,11 @@ static int launch_bwd_lean_b(KDesc d, const BwdPtrs& io, cudaStream_t st) {
 template <int VAR, bool BETAET, int DM, int LAYOUT, bool SIG>
 static int launch_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
     const bool aligned = reinterpret_cast<uintptr_t>(io.dyn) % 8 == 0 && reinterpret_cast<uintptr_t>(io.ckpt) % 16 == 0;
-    return (lean_bwd_ring(d) && aligned) ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 1, LRD_B>(d, io, st)
-                              : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1, 0>(d, io, st);
+    const bool ring = lean_bwd_ring(d) && aligned;
+    // warp-major state store: compiled for the ring form with K = 1 / 4; anything else takes K2
+    if (d.ck_layout != 0 && (!ring || (d.K != 1 && d.K != 4))) return HBV_NOT_ELIGIBLE;
+    return ring ? launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 2, 1, LRD_B>(d, io, st)
+                : launch_bwd_lean_b<VAR, BETAET, DM, LAYOUT, SIG, 8, 1, 0>(d, io, st);
 }
 
 template <int VAR, bool BETAET, int DM>

@@ -692,7 +692,7 @@ static bool pipe_layout_matches(const KDesc& d) {
 static bool pipe_common_ok(const KDesc& d) {
     if (opt(OPT_PIPE) == 0 || opt(OPT_LEAN) == 0) return false;
     if (d.nmul != PNM || d.nvar != 3 || d.i_prcp != 0 || d.i_tmean != 1 || d.i_pet != 2) return false;
-    if (d.T < 2) return false;
+    if (d.T < 2 || d.ck_layout != 0) return false;      // (stored states: plane layout only)
     // Used while the grid leaves schedulers idle (at most one warp per scheduler): there a step's
     // latency IS the kernel time and the skew pays (C2, 531 basins: warm-up 57 -> 44 us, K1 155 ->
     // 137, K2 213 -> 171).  At 2.1 warps per scheduler (BASELINE config 4's per-GPU share, 2,500

@@ -73,6 +73,25 @@ _PIPE_LANES = 148 * 4 * 32                # K1p / K2p regime (csrc/hbv_pipe.cu: 
 BULK_ZERO_FILL = os.environ.get('HBV_B200_BULK_ZERO', '0') == '1'
 
 
+def _ckpt_layout(spec, n_basins: int, K: int) -> int:
+    """hbv_desc_t.ckpt_layout of a training run's state store: warp-major (1) where the
+    standard-layout kernels serve the run with the chunk-ring forward (grids above two warps per
+    scheduler) and K = 1 or 4 — the five states of a stored step then sit at immediate offsets from
+    one pointer (K1s 10, K2s 7 instructions per step less; BASELINE config 4's per-GPU grid: step
+    21.27 -> 20.69 ms).  Planes (0) otherwise: K1p / K2p, the one-warp K1s, and the TMA-staged
+    K1d / K2d (all parameters time-varying) move CTA-wide state rows.  The generic K1 / K2 read
+    either.  Option `ckpt_layout` (HBV_B200_CKPT_LAYOUT) forces 0 / 1."""
+    forced = int(A.load().hbv_b200_get_option(b'ckpt_layout'))
+    if forced in (0, 1):
+        return forced
+    if spec.nmul != 16 or n_basins * spec.nmul <= _SMALL_GRID_LANES or K not in (1, 4):
+        return 0
+    n_dyn = sum(1 for s in spec.par_src[:spec.n_par] if s == A.SRC_DYN_T)
+    if n_dyn == spec.n_par or int(A.load().hbv_b200_get_option(b'dense')) == 2:
+        return 0
+    return 1
+
+
 def _side_stream(dev):
     key = (dev.type, dev.index)
     if key not in _SIDE_STREAMS:
@@ -312,12 +331,18 @@ class _HbvRun(torch.autograd.Function):
         # lane-step stream, and the run stays eligible for the standard-layout kernels.
         alias_series = bool(spec.state_series) and K == 1
         ck_full = None
+        ck_layout = 0
         if alias_series:
             ck_full = torch.empty((T + 1, 5, B, nmul), device=dev, dtype=torch.float32)
             ckpt = ck_full[:T]
         else:
-            ckpt = torch.empty((nseg, 5, B, nmul), device=dev, dtype=torch.float32) if need_grad else None
-            if not need_grad:
+            if need_grad:
+                ck_layout = _ckpt_layout(spec, B, K)
+                d.ckpt_layout = ck_layout
+                lanes = (B * nmul + 31) // 32 * 32 if ck_layout else B * nmul
+                ckpt = torch.empty((nseg * 5 * lanes,), device=dev, dtype=torch.float32)
+            else:
+                ckpt = None
                 d.ckpt_interval = 0
 
         # gradient buffer for `dyn`: zeroed on a side stream, overlapping the forward kernel
@@ -380,6 +405,7 @@ class _HbvRun(torch.autograd.Function):
             torch.cuda.current_stream(dev).wait_event(gev)
         ctx.spec, ctx.t_off, ctx.dims = spec, t_off, (T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
         ctx.K = K
+        ctx.ck_layout = ck_layout
         ctx.has = (dyn is not None, sta is not None)
         ctx.muwts_shape = None if muwts is None else tuple(muwts.shape)
         ctx.gbuf, ctx.gev, ctx.gfused = gbuf, gev, gfused
@@ -483,6 +509,7 @@ class _HbvRun(torch.autograd.Function):
 
             d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
             d.ckpt_interval = ctx.K
+            d.ckpt_layout = ctx.ck_layout
             io = A.HbvBwdIO()
             io.forcing, io.dyn, io.sta = _ptr(forcing), _ptr(dyn[t_off:] if dyn is not None else None), _ptr(sta)
             io.drop, io.attrs, io.muwts, io.ckpt = _ptr(drop), _ptr(attrs), _ptr(mu), _ptr(ckpt)

@@ -117,7 +117,14 @@ typedef struct hbv_desc {
                                       the reference allows 4, hbv_adj.py:518,544) */
     float adj_tol;                 /* HBV_VARIANT_ADJ: ||G||_inf stopping tolerance (0 = default
                                       1e-3, the reference's gtol, hbv_adj.py:519) */
-    int32_t reserved[4];
+    int32_t ckpt_layout;           /* layout of the caller-allocated state store `ckpt` (same value
+                                      in the forward and the backward call; same size either way):
+                                      0 = [ceil(T/K), 5, B, nmul] planes; 1 = warp-major
+                                      [ceil(B*nmul/32)][ceil(T/K)][5][32] — one contiguous 640 B run
+                                      per warp and stored step.  1 is served by the standard-layout
+                                      (K1s / K2s) and the generic (K1 / K2) kernels; not valid together
+                                      with the hbv_2 state series that aliases the store. */
+    int32_t reserved[3];
 } hbv_desc_t;
 
 /* Forward I/O.  NULL output pointers are skipped. */
@@ -375,7 +382,9 @@ HBV_API int hbv_b200_oneshot_allreduce(float* const* peer_bufs_dev, int32_t rank
  * its register form), "lean_small", "lean_bwd_ring", "lean_deep" (largest grid in lanes whose
  * 128-thread K1s takes its inputs through the chunk ring; 0: register prefetch), "dense" (0: never
  * K1d / K2d, 2: wherever the shapes allow), "dense_ns", "dense_ns_bwd", "dense_minb", "ckpt" (the
- * interval hbv_b200_auto_ckpt returns), "adj_bpb" (basins per CTA of K3's forward).  Returns 0, or
+ * interval hbv_b200_auto_ckpt returns), "adj_bpb" (basins per CTA of K3's forward), "copy_blocks"
+ * (hbv_b200_copy_cols: blocks per SM), "ckpt_layout" (read by the Python host side: forces
+ * hbv_desc_t.ckpt_layout).  Returns 0, or
  * HBV_E_SHAPE for an unknown name (get: INT64_MIN). */
 HBV_API int hbv_b200_set_option(const char* name, int64_t value);
 HBV_API int64_t hbv_b200_get_option(const char* name);

@@ -127,7 +127,7 @@ def _reset_library_options():
     if torch.cuda.is_available():
         from hydrodl2_b200 import _cabi
         for name in ('lean', 'pipe', 'pipe_max', 'ring', 'lean_small', 'lean_bwd_ring', 'lean_deep', 'dense',
-                     'dense_ns', 'dense_ns_bwd', 'dense_minb', 'ckpt', 'adj_bpb', 'copy_blocks'):
+                     'dense_ns', 'dense_ns_bwd', 'dense_minb', 'ckpt', 'adj_bpb', 'copy_blocks', 'ckpt_layout'):
             _cabi.set_option(name, -1)
 
 

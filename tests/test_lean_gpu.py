@@ -251,3 +251,54 @@ def test_lean_tiny_shapes(T, B, warm, monkeypatch):
     assert_grad_close(grad, pc.grad, f'tiny T={T} B={B}:grad', NMUL)
     for name, s, r in zip(m.state_names, m.get_states(), ref_states):
         assert_close(s, r, RTOL_FLUX, f'tiny T={T} B={B}:state {name}')
+
+
+@pytest.mark.parametrize('lean,ckpt', [(True, 1), (True, 4), (False, 1), (False, 16)])
+@pytest.mark.parametrize('B', [2500, 2501, 1203])
+def test_state_store_layouts_give_identical_results(B, lean, ckpt, monkeypatch):
+    """hbv_desc_t.ckpt_layout: planes over all lanes (0) or warp-major (1).  Only addresses
+    differ, so outputs and gradients are bit-identical — through K1s / K2s (every-state and
+    segment sweep; chunk-ring and one-warp forward: 2,500 / 1,203 basins; odd B = a half-filled
+    last 32-lane group) and through the generic K1 / K2 (K = 1 ring and K = 16 recompute), which
+    are everyone's fallback."""
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, warm = 29, 4
+    x = O.synthetic_forcing(T, B, seed=51)
+    p = torch.randn(T, B, 13 * NMUL + 2, generator=torch.Generator().manual_seed(52))
+    res = {}
+    for layout in (0, 1):
+        _cabi.set_option('ckpt_layout', layout)
+        n0 = _lean_count()
+        out, grad, _ = _run_packed('hbv', 'Hbv', 13, x, p, dev, lean, monkeypatch, warm, ckpt=ckpt)
+        # (warp-major is compiled for the chunk-ring K1s: on the 1,203-basin grid the forced layout
+        # sends the main forward to K1 — warm-up K1s + K2s remain)
+        want = 0 if not lean else (2 if (layout == 1 and B == 1203) else 3)
+        assert _lean_count() - n0 == want
+        res[layout] = (out['streamflow'].clone(), grad.clone())
+    if lean and B == 1203:      # different kernel families: fp32 contraction noise, not bit-identity
+        assert_close(res[1][0], res[0][0], XTOL, 'layout 1 (K1 + K2s) vs layout 0 (K1s + K2s): streamflow')
+        assert_close(res[1][1], res[0][1], XTOL, 'layout 1 (K1 + K2s) vs layout 0 (K1s + K2s): grad')
+    else:
+        assert torch.equal(res[0][0], res[1][0])
+        assert torch.equal(res[0][1], res[1][1])
+    assert torch.isfinite(res[1][1]).all() and float(res[1][1].abs().max()) > 0
+
+
+def test_state_store_layout_policy():
+    """Warp-major above the stage-pipelined regime for the lean-served sets; planes for the
+    all-dynamic (TMA-staged) set, small grids and the hbv_2 state series."""
+    from hydrodl2_b200 import ops
+    import hydrodl2_b200 as hydrodl2
+    dev = torch.device('cuda:0')
+    M = hydrodl2.load_model('hbv', ver_name='Hbv')
+    m = M({'warm_up': 0, 'dynamic_params': {'Hbv': D2}, 'nmul': NMUL}, device=dev)
+    spec = m._spec(D2, True)
+    assert ops._ckpt_layout(spec, 2500, 1) == 1 and ops._ckpt_layout(spec, 22500, 4) == 1
+    assert ops._ckpt_layout(spec, 531, 1) == 0 and ops._ckpt_layout(spec, 2000, 1) == 0 and ops._ckpt_layout(spec, 2500, 2) == 0
+    M11 = hydrodl2.load_model('hbv_1_1p', ver_name='Hbv_1_1p')
+    names = list(M11({'dynamic_params': {'Hbv_1_1p': []}, 'nmul': NMUL}, device=dev).parameter_bounds.keys())
+    m11 = M11({'warm_up': 0, 'dynamic_params': {'Hbv_1_1p': names}, 'nmul': NMUL}, device=dev)
+    assert ops._ckpt_layout(m11._spec(names, True), 22500, 1) == 0
+    _cabi.set_option('ckpt_layout', 0)
+    assert ops._ckpt_layout(spec, 2500, 1) == 0
