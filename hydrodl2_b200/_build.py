@@ -22,6 +22,11 @@ LIB = os.path.join(LIBDIR, 'libhbv_b200.so')
 SOURCES = ['hbv_cabi.cu', 'hbv_fwd.cu', 'hbv_bwd.cu', 'uh_route.cu', 'pair_route.cu', 'hbv_adj.cu',
            'hbv_dense.cu', 'hbv_lean.cu', 'hbv_pipe.cu', 'fill.cu', 'allreduce.cu']
 HEADERS = ['hbv_step.cuh', 'hbv_common.cuh', os.path.join('..', '..', 'include', 'hbv_b200.h')]
+# Translation units whose explicit template instantiations are compiled as several objects in
+# parallel (-DHBV_TU_PART=k; the source emits all of them when the macro is absent): the
+# standard-layout and the stage-pipelined kernels are a few hundred instantiations each and would
+# otherwise be the critical path of the build.
+PARTS = {'hbv_lean.cu': 4, 'hbv_pipe.cu': 2}
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -61,14 +66,18 @@ def build(force: bool = False, verbose: bool = False, math: int | None = None) -
     procs = []
     tag = '' if math is None else f'_m{math}'
     extra = [] if math is None else [f'-DHBV_MATH={math}']
-    for s in SOURCES:
-        o = os.path.join(LIBDIR, s.replace('.cu', f'{tag}.o'))
-        cmd = [nvcc, *NVCC_FLAGS, *extra, '-c', os.path.join(CSRC, s), '-o', o]
+    units = []          # (source, object suffix, extra defines); the many-instantiation units first
+    for s in sorted(SOURCES, key=lambda n: -PARTS.get(n, 1)):
+        n = PARTS.get(s, 1)
+        units += [(s, '', [])] if n == 1 else [(s, f'_p{k}', [f'-DHBV_TU_PART={k}']) for k in range(1, n + 1)]
+    for s, suffix, defs in units:
+        o = os.path.join(LIBDIR, s.replace('.cu', f'{suffix}{tag}.o'))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, '-c', os.path.join(CSRC, s), '-o', o]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')
             print(' '.join(cmd))
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((s + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
         log, _ = p.communicate()

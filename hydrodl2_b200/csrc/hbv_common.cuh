@@ -30,6 +30,13 @@ struct KDesc {
     float span[HBV_MAX_PAR];  // hi - lo
 };
 
+// A translation unit with many explicit instantiations can be compiled as several objects
+// (-DHBV_TU_PART=k, hydrodl2_b200/_build.py); without the macro it emits all of them.
+#ifndef HBV_TU_PART
+#define HBV_TU_PART 0
+#endif
+#define HBV_IN_PART(k) (HBV_TU_PART == 0 || HBV_TU_PART == (k))
+
 // Stored-state addressing (floats): state s of segment g for global lane L sits at
 //   ck_base(d, L) + (g * 5 + s) * ck_plane(d).
 // Layout 1 gives a warp ONE contiguous 640 B run per stored step (and consecutive steps adjacent)

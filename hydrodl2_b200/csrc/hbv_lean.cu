@@ -861,18 +861,26 @@ int try_bwd_lean(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
 
 // the compiled (variant, dynamic set) pairs: the sets hbv_fwd.cu / hbv_bwd.cu specialise, minus
 // all-dynamic hbv_1_1p (HBM-bound: hbv_dense.cu)
+#if HBV_IN_PART(1)
 template int try_fwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
-template int try_fwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
-template int try_fwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_lean_warm<HBV_VARIANT_HBV, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_lean_warm<HBV_VARIANT_HBV, false>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_lean_warm<HBV_VARIANT_HBV11P, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_lean_warm<HBV_VARIANT_HBV2, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_lean_warm<HBV_VARIANT_HOURLY, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
+#endif
+#if HBV_IN_PART(2)
+template int try_fwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+template int try_fwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
+#endif
+#if HBV_IN_PART(3)
 template int try_bwd_lean<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_lean<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
+#endif
+#if HBV_IN_PART(4)
 template int try_bwd_lean<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_lean<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
+#endif
 
 }  // namespace hbv

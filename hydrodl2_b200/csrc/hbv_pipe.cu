@@ -816,6 +816,7 @@ int try_bwd_pipe(const KDesc& d, const BwdPtrs& io, cudaStream_t st) {
 }
 
 // the compiled (variant, dynamic set) pairs: those of hbv_lean.cu
+#if HBV_IN_PART(1)
 template int try_fwd_pipe<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_pipe<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
 template int try_fwd_pipe<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const FwdPtrs&, bool, cudaStream_t);
@@ -825,9 +826,12 @@ template int try_fwd_pipe_warm<HBV_VARIANT_HBV, false>(const KDesc&, const FwdPt
 template int try_fwd_pipe_warm<HBV_VARIANT_HBV11P, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_pipe_warm<HBV_VARIANT_HBV2, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
 template int try_fwd_pipe_warm<HBV_VARIANT_HOURLY, true>(const KDesc&, const FwdPtrs&, cudaStream_t);
+#endif
+#if HBV_IN_PART(2)
 template int try_bwd_pipe<HBV_VARIANT_HBV, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_pipe<HBV_VARIANT_HBV11P, true, DM_D2>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_pipe<HBV_VARIANT_HBV2, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
 template int try_bwd_pipe<HBV_VARIANT_HOURLY, true, DM_D3>(const KDesc&, const BwdPtrs&, cudaStream_t);
+#endif
 
 }  // namespace hbv
