@@ -480,7 +480,7 @@ def run_b200(args):
                 traffic = None
         r = {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
              'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-             'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'memset + dynamic columns',
+             'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'zero background (memset, or a clean plane kept between steps) + dynamic columns',
              'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
         sb = SURVEY_BYTES.get(traffic_key)
         if sb and kernel in ('hbv_fwd', 'hbv_bwd'):
@@ -581,6 +581,22 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
     ms_step = timed(step_fn, args.steps, args.warmup, sampler, tail=step_tail) / args.steps
     value = world * B * T_MAIN / (ms_step * 1e-3)
+    # The same step with a freshly zeroed dense gradient plane at every step (the clean-plane cache
+    # of ops.py switched off): what the 488 MB memset costs.  In the timed loop above the plane of
+    # the previous step is handed out again without it — nobody references it any more and nobody
+    # modified it in place, and the adjoint rewrites every entry that can be non-zero.
+    ms_memset = None
+    plane_cached = bool(ops.REUSE_GRAD_PLANE and not fused_fill(wl, B) and B * NMUL <= ops._SMALL_GRID_LANES)
+    if plane_cached and world == 1:
+        ops.REUSE_GRAD_PLANE = False
+        try:
+            fn2 = lambda: train_step(model, x_dev, p_dev, allreduce=False)   # noqa: E731
+            if args.graph:
+                from hydrodl2_b200.graphs import GraphedStep
+                fn2 = GraphedStep(fn2, warmup=3, device=dev).replay
+            ms_memset = timed(fn2, args.steps, args.warmup) / args.steps
+        finally:
+            ops.REUSE_GRAD_PLANE = True
     dom = max(kms, key=kms.get)
     roofline = roofline_of(wl, B, kms, dom, traffic_key=args.workload)
     if B * NMUL < 148 * 2048 // 4:
@@ -694,6 +710,10 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_of(wl, B, world),
             'run_info': {'ckpt_interval': k_eff(wl, B), 'launch': graph_note, 'eager_ms_per_step': ms_eager,
+                         'gradient_plane': ('clean plane kept between steps (released + unmodified => no memset; '
+                                            'hydrodl2_b200.ops._clean_plane)' if plane_cached else
+                                            ('zeroed by the adjoint itself' if fused_fill(wl, B) else 'memset every step')),
+                         'ms_per_step_plane_memset_every_step': ms_memset,
                          'shared_grad_allreduce': (('one-shot kernel over NVLink peer memory'
                                                     + (', overlapped with the next step (one step behind)'
                                                        if step_tail is not None else '')) if oneshot else

@@ -155,6 +155,7 @@ class PipelinedSteps:
         self.ev_free = [None] * depth          # compute that last read input set k has finished
         self.ev_out = [None] * depth           # download into host set k has finished
         self.host_out = [None] * depth
+        self._live = [None] * depth            # device results of set k, kept until their download is over
         self.i = 0
 
     def _host_buffers(self, k, outs):
@@ -187,13 +188,18 @@ class PipelinedSteps:
             self.h2d_bytes = moved
             self.ev_in[k].record(self.s_in)
         comp.wait_event(self.ev_in[k])
+        # the host buffers of this set are reused, and so may be the device memory of its previous
+        # results (the library hands a released, unmodified gradient plane out again without
+        # re-zeroing it, ops._clean_plane): their previous download must be over before this
+        # step's kernels are enqueued, and only then are the previous result tensors let go
+        if self.ev_out[k] is not None:
+            self.ev_out[k].synchronize()
+        self._live[k] = None
         outs = self.step_fn(self.dev_in[k])
+        self._live[k] = outs
         ev_done = torch.cuda.Event()
         ev_done.record(comp)
         self.ev_free[k] = ev_done
-        # the host buffers of this set are reused: their previous download must be over
-        if self.ev_out[k] is not None:
-            self.ev_out[k].synchronize()
         hb = self._host_buffers(k, outs)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(ev_done)

@@ -236,7 +236,7 @@ class PackedHbv(PackedSeam, torch.nn.Module):
         gplane = None
         if warm_up > 0:
             # the dense gradient plane starts zeroing while the warm-up kernel runs
-            gplane = start_grad_plane(spec, parameters, warm_up)
+            gplane = start_grad_plane(spec, parameters, warm_up, reusable=(self.dy_drop == 0))
             with torch.no_grad():
                 spec_w = self._spec(dyn_names=(), routing=False)
                 current = hbv_states_only(spec_w, x[:warm_up], parameters[:warm_up].detach(),

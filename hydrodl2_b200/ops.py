@@ -230,7 +230,66 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
     return state_out
 
 
-def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0, _checked: bool = False):
+# ---- clean gradient planes kept between steps ---------------------------------------------------
+# On small, latency-bound grids the dense gradient plane is zeroed by an in-order memset (above):
+# 488 MB = 76 us of BASELINE config 2's 437 us step, although the adjoint rewrites every entry that
+# can be non-zero (the dynamic blocks of the run's rows, the last row) at every step and the rest
+# never changes.  So the library keeps the plane it handed out and hands it out again — WITHOUT the
+# memset — when that is provably the same as a fresh zeroed one:
+#   * same shape / device / run plan (the set of entries the adjoint writes), no dropout mask;
+#   * nobody else references its storage any more (the previous gradient, every view of it, has
+#     been released: torch._C._storage_Use_Count back at the value measured when only the cache
+#     held it);
+#   * it has not been modified in place since (the handed-out tensor is an alias that shares the
+#     cached tensor's version counter; the library's own kernels write through raw pointers).
+# Anything else gets a new zeroed plane.  A plane handed out during CUDA-graph capture is pinned
+# for the life of the process (the graph replays into it).  HBV_B200_REUSE_GRAD_PLANE=0 switches
+# the cache off.
+REUSE_GRAD_PLANE = os.environ.get('HBV_B200_REUSE_GRAD_PLANE', '1') == '1'
+_PLANES: dict = {}          # key -> list of [base tensor, version when clean, storage use count when idle, pinned]
+_PLANES_PER_KEY = 2         # (double-buffered loops keep two gradients alive)
+_PLANE_KEYS = 4             # run plans remembered (oldest forgotten first; pinned planes stay)
+
+
+def _storage_refs(t: torch.Tensor) -> int:
+    return int(torch._C._storage_Use_Count(t.untyped_storage()._cdata))
+
+
+def _clean_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
+    """-> (plane, reused): an alias of a cached clean plane, or a new zeroed one (now cached)."""
+    key = (dyn.device, tuple(dyn.shape), t_off, spec.variant, spec.nmul, spec.n_par, tuple(spec.par_src[:spec.n_par]),
+           tuple(spec.par_col[:spec.n_par]), spec.routing, spec.route_src, spec.route_col)
+    ents = _PLANES.get(key)
+    if ents is None:
+        ents = _PLANES[key] = []
+        for k in list(_PLANES)[:-_PLANE_KEYS]:            # forget the oldest run plans' idle planes
+            _PLANES[k] = [e for e in _PLANES[k] if e[3]]
+            if not _PLANES[k]:
+                del _PLANES[k]
+    capturing = torch.cuda.is_current_stream_capturing()
+    for e in ents:
+        base, ver, idle, pinned = e
+        if not pinned and base._version == ver and _storage_refs(base) == idle:
+            if capturing:
+                e[3] = True
+            out = base.detach()
+            out._hbv_clean_plane = True
+            return out, True
+    base = torch.zeros_like(dyn, requires_grad=False)
+    ent = [base, base._version, _storage_refs(base), capturing]
+    ents.append(ent)
+    if sum(1 for e in ents if not e[3]) > _PLANES_PER_KEY:       # forget the oldest plane no graph replays into
+        for i, e in enumerate(ents):
+            if not e[3] and e is not ent:
+                del ents[i]
+                break
+    out = base.detach()
+    out._hbv_clean_plane = True
+    return out, False
+
+
+def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0, _checked: bool = False,
+                     reusable: bool = True):
     """Allocate the dense gradient plane of `dyn` and start zeroing what the adjoint will not write
     on the side stream right away: everything (memset mode) or, when the adjoint writes its rows
     itself, the warm-up rows [:t_off] and the routing columns of the last row.  A model with a
@@ -246,6 +305,10 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0,
     if fused and dyn.shape[1] * spec.nmul <= _PIPE_LANES:
         return None           # K2p zeroes the warm-up rows itself (gdyn_rows_before, see backward)
     dev = dyn.device
+    small = dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES
+    if small and not fused and not THIN_FILL and reusable and REUSE_GRAD_PLANE:
+        gbuf, _ = _clean_plane(spec, dyn, t_off)
+        return gbuf, None, fused
     gbuf = torch.empty_like(dyn)
 
     def fill():
@@ -256,7 +319,6 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0,
         else:
             gbuf.zero_()
 
-    small = dyn.shape[1] * spec.nmul <= _SMALL_GRID_LANES
     if small and THIN_FILL:
         # Latency-bound regime (a warp or two per scheduler): a full-occupancy memset running next
         # to the recurrence kernels starves them for longer than the fill itself takes (C2: a 76 us
@@ -350,7 +412,7 @@ class _HbvRun(torch.autograd.Function):
         gfused = False
         if need_grad and dyn is not None and dyn.requires_grad:
             if gplane is None:
-                gplane = start_grad_plane(spec, dyn, t_off, _checked=True)
+                gplane = start_grad_plane(spec, dyn, t_off, _checked=True, reusable=drop is None)
             if gplane is not None:
                 gbuf, gev, gfused = gplane    # (possibly started before the warm-up kernel)
 
@@ -464,6 +526,7 @@ class _HbvRun(torch.autograd.Function):
             gdyn_run = gdyn_full[t_off:]
         gsta = torch.zeros_like(sta) if sta is not None else None
 
+        routed_grads = False
         with torch.cuda.device(dev):
             if spec.routing and (any(g is not None for g in g_rout) or g_bfi is not None):
                 mask = 0
@@ -498,6 +561,7 @@ class _HbvRun(torch.autograd.Function):
                         C.byref(rdesc), route_t.data_ptr(), flux.data_ptr(), T * B, None, T * B,
                         uh.data_ptr(), _ptr(bfi_ws), g_out_ptr, T * B, mask, _ptr(gb),
                         g_in.data_ptr(), T * B, g_route.data_ptr(), ws.data_ptr(), stream), 'route_bwd')
+                routed_grads = True
                 for s in range(n_r):
                     # a series without upstream gradient (and no BFI term) has an all-zero
                     # adjoint plane: do not make K2 read it
@@ -507,6 +571,12 @@ class _HbvRun(torch.autograd.Function):
                     f = _ROUTED[s]
                     g_flux[f] = g_in[s] if g_flux[f] is None else g_flux[f] + g_in[s]
 
+            if (gdyn_full is not None and getattr(gdyn_full, '_hbv_clean_plane', False) and not routed_grads
+                    and spec.routing and spec.route_src == 'dyn_last' and spec.route_col < dyn_ncol):
+                # a plane from the clean-plane cache whose routing columns nobody writes in this
+                # backward (no routed cotangent): they may hold an earlier step's gradient.  The
+                # in-place op also bumps the plane's version counter, so the cache lets go of it.
+                gdyn_full[dyn.shape[0] - 1, :, spec.route_col:].zero_()
             d = make_desc(spec, T, B, nvar, dyn_ncol, sta_ncol, mu_ts)
             d.ckpt_interval = ctx.K
             d.ckpt_layout = ctx.ck_layout
