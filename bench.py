@@ -467,9 +467,12 @@ def run_b200(args):
         spec = Model(model_config(wl), device=dev)._spec(wl['dyn'], True)
         return bool(ops._fused_zero_fill(spec, wl['n_par'] * NMUL + 2, B))
 
+    def rows_written(wl, B):   # ... in the timed steps: not when a clean plane is kept between them
+        return fused_fill(wl, B) and not ops.REUSE_GRAD_PLANE
+
     def roofline_of(wl, B, kms, kernel, traffic_key=None):
         units = B * (wl['T'] if kernel != 'hbv_fwd_warmup' else wl['warm_up'])
-        per_unit = per_unit_bytes(wl, k_eff(wl, B), fused_fill(wl, B))[kernel]
+        per_unit = per_unit_bytes(wl, k_eff(wl, B), rows_written(wl, B))[kernel]
         achieved = per_unit * units / (kms[kernel] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -480,7 +483,8 @@ def run_b200(args):
                 traffic = None
         r = {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
              'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-             'gradient_plane': 'written by the adjoint' if fused_fill(wl, B) else 'zero background (memset, or a clean plane kept between steps) + dynamic columns',
+             'gradient_plane': ('dense rows written by the adjoint' if rows_written(wl, B) else
+                                'zero background (a clean plane kept between steps, else a memset / the adjoint\'s own zero fill) + dynamic columns'),
              'algorithmic_bytes_per_basin_step': per_unit, 'kernel_ms': kms[kernel]}
         sb = SURVEY_BYTES.get(traffic_key)
         if sb and kernel in ('hbv_fwd', 'hbv_bwd'):
@@ -586,7 +590,7 @@ def run_b200(args):
     # the previous step is handed out again without it — nobody references it any more and nobody
     # modified it in place, and the adjoint rewrites every entry that can be non-zero.
     ms_memset = None
-    plane_cached = bool(ops.REUSE_GRAD_PLANE and not fused_fill(wl, B) and B * NMUL <= ops._SMALL_GRID_LANES)
+    plane_cached = bool(ops.REUSE_GRAD_PLANE)
     if plane_cached and world == 1:
         ops.REUSE_GRAD_PLANE = False
         try:
@@ -613,6 +617,7 @@ def run_b200(args):
     if not x_host.is_cuda:   # shard-sized inputs are generated on the device: no host copy to time
         e2e = _e2e(args, dev, world, wl, B, model, x_host, p_host, x_dev, p_dev, train_step, timed)
     del x_dev, p_dev, x_host, p_host, model
+    ops.release_grad_planes()      # (idle cached gradient planes of the finished workload)
     torch.cuda.empty_cache()
 
     # ---------------- north-star per-GPU shards ----------------
@@ -627,15 +632,26 @@ def run_b200(args):
             s_steps, s_warm = 5, 3
             ms_s, kms_s = timed_with_kernels(lambda: train_step(model_s, xs, ps), s_steps, s_warm)
             ms_sf, kms_sf = timed_with_kernels(lambda: fwd_only(model_s, xs, ps), s_steps, s_warm)
+            ms_s_fill = None          # the same step with the dense plane (re)written at every step
+            if ops.REUSE_GRAD_PLANE:
+                ops.REUSE_GRAD_PLANE = False
+                try:
+                    ps.grad = None
+                    ops.release_grad_planes()
+                    ms_s_fill = timed(lambda: train_step(model_s, xs, ps), s_steps, s_warm) / s_steps
+                finally:
+                    ops.REUSE_GRAD_PLANE = True
             at_scale[name] = {
                 'workload': describe(w2, Bs),
                 'value': world * Bs * w2['T'] / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
+                'ms_per_step_plane_rewritten_every_step': ms_s_fill,
                 'fwd_value': world * Bs * w2['T'] / (ms_sf * 1e-3), 'fwd_ms_per_step': ms_sf,
                 'kernel_ms': kms_s, 'fwd_kernel_ms': kms_sf,
                 'roofline': roofline_of(w2, Bs, kms_s, 'hbv_bwd', traffic_key=name),
                 'roofline_fwd': roofline_of(w2, Bs, kms_s, 'hbv_fwd', traffic_key=name),
             }
             del model_s, xs, ps
+            ops.release_grad_planes()      # (idle cached gradient planes of the finished workload)
             torch.cuda.empty_cache()
 
     # BASELINE configs[3] and [4] at their per-GPU sizes (scripts/bench_configs.py): c4 = hbv_2_hourly,
@@ -651,6 +667,7 @@ def run_b200(args):
                 res = fn(3, dev=dev, seed_offset=rank, **kw)
             except Exception as exc:      # pragma: no cover - keep the bench line alive
                 at_scale[name] = {'error': f'{type(exc).__name__}: {exc}'}
+                ops.release_grad_planes()      # (idle cached gradient planes of the finished workload)
                 torch.cuda.empty_cache()
                 continue
             ms_max = D.max_over_ranks(res['ms_per_step'], dev)
@@ -670,6 +687,7 @@ def run_b200(args):
                     entry[leg]['algorithmic_bytes_survey'] = by['survey']
                     entry[leg]['frac_survey'] = by['survey'] * res['units_per_gpu'] / (res['kernel_ms'][kern] * 1e-3) / 1e9 / peak
             at_scale[name] = entry
+            ops.release_grad_planes()      # (idle cached gradient planes of the finished workload)
             torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
@@ -710,8 +728,8 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config_of(wl, B, world),
             'run_info': {'ckpt_interval': k_eff(wl, B), 'launch': graph_note, 'eager_ms_per_step': ms_eager,
-                         'gradient_plane': ('clean plane kept between steps (released + unmodified => no memset; '
-                                            'hydrodl2_b200.ops._clean_plane)' if plane_cached else
+                         'gradient_plane': ('clean plane kept between steps (released + unmodified => no memset / no '
+                                            'zero fill by the adjoint; hydrodl2_b200.ops._clean_plane)' if plane_cached else
                                             ('zeroed by the adjoint itself' if fused_fill(wl, B) else 'memset every step')),
                          'ms_per_step_plane_memset_every_step': ms_memset,
                          'shared_grad_allreduce': (('one-shot kernel over NVLink peer memory'

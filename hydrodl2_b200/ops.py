@@ -255,17 +255,30 @@ def _storage_refs(t: torch.Tensor) -> int:
     return int(torch._C._storage_Use_Count(t.untyped_storage()._cdata))
 
 
-def _clean_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
-    """-> (plane, reused): an alias of a cached clean plane, or a new zeroed one (now cached)."""
-    key = (dyn.device, tuple(dyn.shape), t_off, spec.variant, spec.nmul, spec.n_par, tuple(spec.par_src[:spec.n_par]),
-           tuple(spec.par_col[:spec.n_par]), spec.routing, spec.route_src, spec.route_col)
-    ents = _PLANES.get(key)
-    if ents is None:
-        ents = _PLANES[key] = []
-        for k in list(_PLANES)[:-_PLANE_KEYS]:            # forget the oldest run plans' idle planes
-            _PLANES[k] = [e for e in _PLANES[k] if e[3]]
-            if not _PLANES[k]:
-                del _PLANES[k]
+# idle planes kept in total, bytes (a 22,500-basin shard's plane is 20.7 GB); HBV_B200_PLANE_CACHE_GB
+_PLANE_BYTES_MAX = int(float(os.environ.get('HBV_B200_PLANE_CACHE_GB', '48')) * (1 << 30))
+
+
+def release_grad_planes() -> None:
+    """Let go of every cached gradient plane no CUDA graph replays into (their memory returns to
+    PyTorch's allocator once the last gradient aliasing them is released)."""
+    for k in list(_PLANES):
+        _PLANES[k] = [e for e in _PLANES[k] if e[3]]
+        if not _PLANES[k]:
+            del _PLANES[k]
+
+
+
+def _plane_key(spec: RunSpec, dyn: torch.Tensor, t_off: int):
+    return (dyn.device, tuple(dyn.shape), t_off, spec.variant, spec.nmul, spec.n_par, tuple(spec.par_src[:spec.n_par]),
+            tuple(spec.par_col[:spec.n_par]), spec.routing, spec.route_src, spec.route_col)
+
+
+def _lookup_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
+    """An alias of a cached plane that is provably clean, or None."""
+    ents = _PLANES.get(_plane_key(spec, dyn, t_off))
+    if not ents:
+        return None
     capturing = torch.cuda.is_current_stream_capturing()
     for e in ents:
         base, ver, idle, pinned = e
@@ -274,18 +287,49 @@ def _clean_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
                 e[3] = True
             out = base.detach()
             out._hbv_clean_plane = True
-            return out, True
-    base = torch.zeros_like(dyn, requires_grad=False)
-    ent = [base, base._version, _storage_refs(base), capturing]
+            return out
+    return None
+
+
+def _register_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int, base: torch.Tensor):
+    """Remember `base` — every entry of it initialised, only this reference to its storage alive —
+    and return the alias to hand out."""
+    key = _plane_key(spec, dyn, t_off)
+    nbytes = base.numel() * base.element_size()
+    if nbytes > _PLANE_BYTES_MAX:
+        return base
+    ents = _PLANES.get(key)
+    if ents is None:
+        ents = _PLANES[key] = []
+        for k in list(_PLANES)[:-_PLANE_KEYS]:            # forget the oldest run plans' idle planes
+            _PLANES[k] = [e for e in _PLANES[k] if e[3]]
+            if not _PLANES[k]:
+                del _PLANES[k]
+    ent = [base, base._version, _storage_refs(base), torch.cuda.is_current_stream_capturing()]
     ents.append(ent)
-    if sum(1 for e in ents if not e[3]) > _PLANES_PER_KEY:       # forget the oldest plane no graph replays into
-        for i, e in enumerate(ents):
-            if not e[3] and e is not ent:
-                del ents[i]
-                break
+    per_key = 1 if nbytes > (2 << 30) else _PLANES_PER_KEY
+    while sum(1 for e in ents if not e[3]) > per_key:            # forget the oldest plane no graph replays into
+        i = next(i for i, e in enumerate(ents) if not e[3] and e is not ent)
+        del ents[i]
+
+    def idle_bytes():
+        return sum(e[0].numel() * 4 for v in _PLANES.values() for e in v if not e[3])
+    for k in list(_PLANES):                                      # total budget: oldest run plans first
+        if idle_bytes() <= _PLANE_BYTES_MAX:
+            break
+        if k != key:
+            _PLANES[k] = [e for e in _PLANES[k] if e[3]]
     out = base.detach()
     out._hbv_clean_plane = True
-    return out, False
+    return out
+
+
+def _clean_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
+    """-> (plane, reused): an alias of a cached clean plane, or a new zeroed one (now cached)."""
+    hit = _lookup_plane(spec, dyn, t_off)
+    if hit is not None:
+        return hit, True
+    return _register_plane(spec, dyn, t_off, torch.zeros_like(dyn, requires_grad=False)), False
 
 
 def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0, _checked: bool = False,
@@ -300,6 +344,12 @@ def start_grad_plane(spec: RunSpec, dyn: Optional[torch.Tensor], t_off: int = 0,
         if dyn is None or not dyn.is_cuda or not (torch.is_grad_enabled() and dyn.requires_grad):
             return None
     fused = _fused_zero_fill(spec, dyn.shape[-1], dyn.shape[1])
+    if fused and reusable and REUSE_GRAD_PLANE:
+        # the adjoint would write every element of the run's rows itself (zeros included); a clean
+        # plane kept from an earlier step needs none of that: the adjoint writes its entries only
+        hit = _lookup_plane(spec, dyn, t_off)
+        if hit is not None:
+            return hit, None, False
     if fused and t_off == 0:
         return None           # only the routing columns of one row: the backward clears them in order
     if fused and dyn.shape[1] * spec.nmul <= _PIPE_LANES:
@@ -527,6 +577,7 @@ class _HbvRun(torch.autograd.Function):
         gsta = torch.zeros_like(sta) if sta is not None else None
 
         routed_grads = False
+        g_route = None
         with torch.cuda.device(dev):
             if spec.routing and (any(g is not None for g in g_rout) or g_bfi is not None):
                 mask = 0
@@ -605,6 +656,14 @@ class _HbvRun(torch.autograd.Function):
             gmu = gmu.view((-1, B, nmul) if mu_ts else (1, B, nmul)).sum_to_size(ctx.muwts_shape)
         if not (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
             gdyn_full = gsta = None
+        if (REUSE_GRAD_PLANE and gdyn_full is not None and zero_fill == 1 and drop is None
+                and not getattr(gdyn_full, '_hbv_clean_plane', False)):
+            # this call has initialised every element of the plane (the adjoint's fused zero fill +
+            # the warm-up rows / routing columns cleared above): keep it, so that the next step with
+            # the same run plan can skip all of that (ops._clean_plane; the views must go first —
+            # the cache remembers how many references the idle plane has)
+            gdyn_run = g_route = None
+            gdyn_full = _register_plane(spec, dyn, t_off, gdyn_full)
         return (None, gforcing, gdyn_full, gsta, gstate_in, None, None, gmu, None, None, None)
 
 
@@ -753,9 +812,16 @@ class _HbvAdjRun(torch.autograd.Function):
         # routing columns of the last row of each call's slice — is cleared here.
         nmul = spec.nmul
         fused = nmul == 16 and ncol % 2 == 0
-        if fused:
+        n_phy = spec.n_par * nmul
+        kept = None
+        if fused and REUSE_GRAD_PLANE and drop is None:
+            kept = _lookup_plane(spec, dyn, warm_up)      # a clean plane kept from an earlier step (see _clean_plane)
+        if kept is not None:
+            gdyn, fused = kept, False                     # the adjoint writes its gradient entries only
+            if not (spec.routing and g_rout is not None) and n_phy < ncol:
+                gdyn[Tt - 1, :, n_phy:].zero_()           # nobody writes the routing columns this time (retires the plane)
+        elif fused:
             gdyn = torch.empty_like(dyn)
-            n_phy = spec.n_par * nmul
             gdyn[Tt - 1, :, n_phy:].zero_()
             if warm_up > 0:
                 gdyn[warm_up - 1, :, n_phy:].zero_()
@@ -804,6 +870,9 @@ class _HbvAdjRun(torch.autograd.Function):
                 io.gdyn_zero_fill = int(fused)
                 with _timed('hbv_adj_bwd_warmup', dev):
                     A.check(lib.hbv_b200_adj_bwd(C.byref(desc_of(spec_w, warm_up)), C.byref(io), stream), 'adj_bwd(warm-up)')
+        if fused and kept is None and REUSE_GRAD_PLANE and drop is None:
+            g_route = route_t = io = None                 # (views of the plane: the cache counts references)
+            gdyn = _register_plane(spec, dyn, warm_up, gdyn)
         return (None, None, None, gdyn, gstate_in if state_in.requires_grad else None, None, None, None, None)
 
 

@@ -200,6 +200,8 @@ def main():
         res = {'c4': run_c4, 'c5': run_c5}[w](steps)
         res['wall_s'] = time.time() - t0
         print(json.dumps(res), flush=True)
+        from hydrodl2_b200 import ops
+        ops.release_grad_planes()      # (idle cached gradient planes of the finished workload)
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
 

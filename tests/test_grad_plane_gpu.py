@@ -127,3 +127,62 @@ def test_plane_cache_under_cuda_graph():
     assert len(pinned) == 1
     g_eager = _grad(m, x, ps[0])
     assert torch.equal(g_eager, ref[0]) and g_eager.data_ptr() != g.data_ptr()
+
+
+def test_fused_zero_fill_plane_is_kept_and_reused_on_large_grids():
+    """Above the small-grid regime the adjoint zeroes its rows itself; the plane it initialised is
+    kept, and the next step writes the gradient entries only (no zero fill, no memset) — same
+    gradients bit for bit, with and without a warm-up period."""
+    from hydrodl2_b200 import ops
+    for warm in (5, 0):
+        m, x, ps = _setup(T=23, B=2501, warm=warm, seed=17 + warm)
+        ref = _reference_grads(m, x, ps, ['streamflow'] * 3)
+        ops.release_grad_planes()
+        ptrs = []
+        for p, r in zip(ps, ref):
+            g = _grad(m, x, p)
+            assert torch.equal(g, r)
+            ptrs.append(g.data_ptr())
+            del g
+        assert ptrs[0] == ptrs[1] == ptrs[2]
+        g = _grad(m, x, ps[0], 'streamflow_no_rout')       # no routed cotangent: routing columns zeroed
+        assert float(g[-1, :, 13 * NMUL:].abs().max()) == 0.0
+        del g
+    ops.release_grad_planes()
+    assert all(e[3] for v in ops._PLANES.values() for e in v)      # (planes a CUDA graph replays into stay)
+
+
+@pytest.mark.parametrize('warm', [0, 9])
+def test_hbv_adj_plane_is_kept_and_reused(warm):
+    """The implicit scheme's adjoint (K3) zero-fills its rows itself; the plane it initialised is
+    kept and the next steps write gradient entries only — bit-identical gradients."""
+    import hydrodl2_b200 as hydrodl2
+    from hydrodl2_b200 import ops
+    from oracle import hbv_oracle as O
+    dev = torch.device('cuda:0')
+    T, B = 31, 21
+    M = hydrodl2.load_model('hbv_adj', ver_name='HbvAdj')
+    m = M({'warm_up': warm, 'dynamic_params': {'HbvAdj': D2}, 'nmul': NMUL}, device=dev)
+    x = O.synthetic_forcing(T, B, seed=23).to(dev)
+    g = torch.Generator().manual_seed(24)
+    ps = [torch.randn(T, B, 13 * NMUL + 2, generator=g).to(dev) for _ in range(3)]
+
+    def grad(p):
+        pg = p.clone().requires_grad_(True)
+        m({'x_phy': x}, pg)['flow_sim'].sum().backward()
+        return pg.grad
+
+    ops.REUSE_GRAD_PLANE = False
+    try:
+        ref = [grad(p).clone() for p in ps]
+    finally:
+        ops.REUSE_GRAD_PLANE = True
+    ops.release_grad_planes()
+    ptrs = []
+    for p, r in zip(ps, ref):
+        gg = grad(p)
+        assert torch.equal(gg, r)
+        ptrs.append(gg.data_ptr())
+        del gg
+    assert ptrs[0] == ptrs[1] == ptrs[2]
+    ops.release_grad_planes()
