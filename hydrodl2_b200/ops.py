@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -246,6 +247,7 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
 # for the life of the process (the graph replays into it).  HBV_B200_REUSE_GRAD_PLANE=0 switches
 # the cache off.
 REUSE_GRAD_PLANE = os.environ.get('HBV_B200_REUSE_GRAD_PLANE', '1') == '1'
+_PLANES_LOCK = threading.RLock()
 _PLANES: dict = {}          # key -> list of [base tensor, version when clean, storage use count when idle, pinned]
 _PLANES_PER_KEY = 2         # (double-buffered loops keep two gradients alive)
 _PLANE_KEYS = 4             # run plans remembered (oldest forgotten first; pinned planes stay)
@@ -262,10 +264,11 @@ _PLANE_BYTES_MAX = int(float(os.environ.get('HBV_B200_PLANE_CACHE_GB', '48')) * 
 def release_grad_planes() -> None:
     """Let go of every cached gradient plane no CUDA graph replays into (their memory returns to
     PyTorch's allocator once the last gradient aliasing them is released)."""
-    for k in list(_PLANES):
-        _PLANES[k] = [e for e in _PLANES[k] if e[3]]
-        if not _PLANES[k]:
-            del _PLANES[k]
+    with _PLANES_LOCK:
+        for k in list(_PLANES):
+            _PLANES[k] = [e for e in _PLANES[k] if e[3]]
+            if not _PLANES[k]:
+                del _PLANES[k]
 
 
 
@@ -276,19 +279,20 @@ def _plane_key(spec: RunSpec, dyn: torch.Tensor, t_off: int):
 
 def _lookup_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int):
     """An alias of a cached plane that is provably clean, or None."""
-    ents = _PLANES.get(_plane_key(spec, dyn, t_off))
-    if not ents:
+    with _PLANES_LOCK:
+        ents = _PLANES.get(_plane_key(spec, dyn, t_off))
+        if not ents:
+            return None
+        capturing = torch.cuda.is_current_stream_capturing()
+        for e in ents:
+            base, ver, idle, pinned = e
+            if not pinned and base._version == ver and _storage_refs(base) == idle:
+                if capturing:
+                    e[3] = True
+                out = base.detach()
+                out._hbv_clean_plane = True
+                return out
         return None
-    capturing = torch.cuda.is_current_stream_capturing()
-    for e in ents:
-        base, ver, idle, pinned = e
-        if not pinned and base._version == ver and _storage_refs(base) == idle:
-            if capturing:
-                e[3] = True
-            out = base.detach()
-            out._hbv_clean_plane = True
-            return out
-    return None
 
 
 def _register_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int, base: torch.Tensor):
@@ -298,6 +302,11 @@ def _register_plane(spec: RunSpec, dyn: torch.Tensor, t_off: int, base: torch.Te
     nbytes = base.numel() * base.element_size()
     if nbytes > _PLANE_BYTES_MAX:
         return base
+    with _PLANES_LOCK:
+        return _register_plane_locked(key, nbytes, base)
+
+
+def _register_plane_locked(key, nbytes: int, base: torch.Tensor):
     ents = _PLANES.get(key)
     if ents is None:
         ents = _PLANES[key] = []
