@@ -246,7 +246,9 @@ def hbv_states_only(spec: RunSpec, forcing, dyn, sta, state_in, drop=None, attrs
 # Anything else gets a new zeroed plane.  A plane handed out during CUDA-graph capture is pinned
 # for the life of the process (the graph replays into it).  HBV_B200_REUSE_GRAD_PLANE=0 switches
 # the cache off.
-REUSE_GRAD_PLANE = os.environ.get('HBV_B200_REUSE_GRAD_PLANE', '1') == '1'
+# (needs torch's storage use count; without that private hook every step gets a fresh plane)
+REUSE_GRAD_PLANE = (os.environ.get('HBV_B200_REUSE_GRAD_PLANE', '1') == '1'
+                    and hasattr(torch._C, '_storage_Use_Count'))
 _PLANES_LOCK = threading.RLock()
 _PLANES: dict = {}          # key -> list of [base tensor, version when clean, storage use count when idle, pinned]
 _PLANES_PER_KEY = 2         # (double-buffered loops keep two gradients alive)
